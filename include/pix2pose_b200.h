@@ -1,0 +1,77 @@
+/* pix2pose_b200 -- C ABI of the B200-native Pix2Pose per-detection inference hot path.
+ *
+ * The reference (kirumang/Pix2Pose) is pure Python and has no FFI; the boundary it exposes is the
+ * class `pix2pose` of pix2pose_model/recognition.py and the Keras `generator_train` duck type
+ * (`load_weights`, `predict`).  Each entry point below names the reference call it replaces.
+ * pix2pose_b200/{recognition,ae_model}.py bind these through ctypes.
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer it passes; handles own their
+ * device memory; every function returns 0 (P2P_OK) or a negative status and never throws --
+ * `p2p_last_error()` returns the message of the last failure on the calling thread.  There is no
+ * CPU fallback: without an sm_100 device, creation fails with P2P_ERR_NO_DEVICE.
+ */
+#ifndef PIX2POSE_B200_H
+#define PIX2POSE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define P2P_API __attribute__((visibility("default")))
+#else
+#define P2P_API
+#endif
+
+#define P2P_OK 0
+#define P2P_ERR_INVALID (-1)
+#define P2P_ERR_CUDA (-2)
+#define P2P_ERR_NO_DEVICE (-3)
+#define P2P_ERR_INTERNAL (-4)
+
+#define P2P_PREC_FP16X3 0 /* fp16 hi/lo operand pairs, 3 MMAs per k-step: matches fp32 to ~1e-5 (default) */
+#define P2P_PREC_FP16 1   /* plain fp16 operands: ~3x faster contractions, ~1e-2 max abs error      */
+
+typedef struct p2p_engine p2p_engine_t; /* per device: activation workspace + plan for one backbone   */
+typedef struct p2p_model p2p_model_t;   /* per object: packed weights (reference keeps one Keras model
+                                           per object id, tools/5_evaluation_bop_basic.py:206-225)   */
+
+P2P_API const char* p2p_last_error(void);
+P2P_API const char* p2p_version(void);
+
+/* Number of fp32 values in a weight blob for `backbone` ("resnet50" | "paper"): all tensors of
+ * pix2pose_b200/weights.py:param_names(backbone), Keras layouts, concatenated in that order
+ * (= the order Model.load_weights walks an inference*.hdf5, recognition.py:23-26). 0 on error. */
+P2P_API size_t p2p_param_count(const char* backbone);
+/* Algorithmic FLOPs (2*MAC) of one 128x128 forward; 0 on error. */
+P2P_API double p2p_flops_per_crop(const char* backbone);
+
+/* ae.aemodel_unet_resnet50(p) / ae.aemodel_unet_prob(p) (ae_model.py:175, :70): builds the graph
+ * for batches of up to `capacity` crops on the current CUDA device. */
+P2P_API int p2p_engine_create(const char* backbone, int capacity, int precision, p2p_engine_t** out);
+P2P_API void p2p_engine_destroy(p2p_engine_t* e);
+P2P_API int p2p_engine_capacity(const p2p_engine_t* e);
+P2P_API long long p2p_engine_launch_count(const p2p_engine_t* e);
+
+/* generator_train.load_weights(weight_fn) (recognition.py:23,26) after the file has been parsed
+ * on the host: `blob` holds p2p_param_count() floats. BN is folded, kernels are repacked. */
+P2P_API int p2p_model_create(p2p_engine_t* e, const float* blob, size_t n_floats, p2p_model_t** out);
+P2P_API void p2p_model_destroy(p2p_model_t* m);
+
+/* generator_train.predict(x) (recognition.py:84,129): x (n,128,128,3) fp32 NHWC host memory ->
+ * decode (n,128,128,3) tanh, prob (n,128,128,1) sigmoid, host memory. Any n >= 0 (chunked). */
+P2P_API int p2p_predict(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, float* decode, float* prob);
+/* Same with device pointers on `stream` (a cudaStream_t, may be NULL), n <= capacity, asynchronous. */
+P2P_API int p2p_predict_device(p2p_engine_t* e, const p2p_model_t* m, const float* x_dev, int n, float* decode_dev,
+                       float* prob_dev, void* stream);
+
+/* Debug/parity: copy intermediate activation `name` (e.g. "f1", "act3d", "d2_uni") of the last
+ * forward as (n,H,W,C) fp32; *h,*w,*c receive the shape. `out` may be NULL to query the shape. */
+P2P_API int p2p_engine_read_tensor(p2p_engine_t* e, const char* name, int n, float* out, int* h, int* w, int* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIX2POSE_B200_H */

@@ -1,0 +1,79 @@
+"""ctypes binding of libpix2pose_b200.so (include/pix2pose_b200.h).  Fails loudly: no CPU fallback."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpix2pose_b200.so")
+
+P2P_OK = 0
+PREC_FP16X3 = 0
+PREC_FP16 = 1
+_PRECISIONS = {"fp16x3": PREC_FP16X3, "fp16": PREC_FP16}
+
+_lib = None
+
+
+class P2PError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pix2pose_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def precision_code(p):
+    if isinstance(p, str):
+        if p not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        return _PRECISIONS[p]
+    return int(p)
+
+
+def lib():
+    """Loads the shared library (building it is `__graft_entry__.build()` / csrc/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -m pix2pose_b200.csrc.build` "
+                          "(nvcc, sm_100a). pix2pose_b200 has no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_f = ctypes.POINTER(ctypes.c_float)
+    c_d = ctypes.POINTER(ctypes.c_double)
+    c_i = ctypes.POINTER(ctypes.c_int)
+    vp = ctypes.c_void_p
+    sig = {
+        "p2p_last_error": (ctypes.c_char_p, []),
+        "p2p_version": (ctypes.c_char_p, []),
+        "p2p_param_count": (ctypes.c_size_t, [ctypes.c_char_p]),
+        "p2p_flops_per_crop": (ctypes.c_double, [ctypes.c_char_p]),
+        "p2p_engine_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+        "p2p_engine_destroy": (None, [vp]),
+        "p2p_engine_capacity": (ctypes.c_int, [vp]),
+        "p2p_engine_launch_count": (ctypes.c_longlong, [vp]),
+        "p2p_model_create": (ctypes.c_int, [vp, c_f, ctypes.c_size_t, ctypes.POINTER(vp)]),
+        "p2p_model_destroy": (None, [vp]),
+        "p2p_predict": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, c_f, c_f]),
+        "p2p_predict_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
+        "p2p_engine_read_tensor": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int, c_f, c_i, c_i, c_i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._sig_names = sorted(sig)
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != P2P_OK:
+        raise P2PError(code, lib().p2p_last_error().decode("utf-8", "replace"))
+
+
+def fptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def as_f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)

@@ -1,0 +1,79 @@
+// C ABI (include/pix2pose_b200.h) over the engine.  No exception crosses this boundary.
+#include "../../include/pix2pose_b200.h"
+
+#include "engine.cuh"
+
+using namespace p2p;
+
+struct p2p_engine { std::unique_ptr<Engine> e; };
+struct p2p_model { std::unique_ptr<Model> m; };
+
+extern "C" {
+
+const char* p2p_last_error(void) { return get_last_error(); }
+const char* p2p_version(void) { return "pix2pose_b200 0.1 (sm_100a)"; }
+
+size_t p2p_param_count(const char* backbone) {
+    size_t n = 0;
+    guarded([&] { n = param_count(parse_backbone(backbone)); });
+    return n;
+}
+
+double p2p_flops_per_crop(const char* backbone) {
+    double f = 0;
+    guarded([&] { f = build_plan(parse_backbone(backbone)).flops_per_crop(); });
+    return f;
+}
+
+int p2p_engine_create(const char* backbone, int capacity, int precision, p2p_engine_t** out) {
+    return guarded([&] {
+        P2P_CHECK(out != nullptr, "out is NULL");
+        *out = nullptr;
+        std::unique_ptr<p2p_engine> h(new p2p_engine);
+        h->e.reset(new Engine(parse_backbone(backbone), capacity, precision));
+        *out = h.release();
+    });
+}
+void p2p_engine_destroy(p2p_engine_t* e) { delete e; }
+int p2p_engine_capacity(const p2p_engine_t* e) { return e ? e->e->cap : 0; }
+long long p2p_engine_launch_count(const p2p_engine_t* e) { return e ? e->e->launches : 0; }
+
+int p2p_model_create(p2p_engine_t* e, const float* blob, size_t n_floats, p2p_model_t** out) {
+    return guarded([&] {
+        P2P_CHECK(e && blob && out, "NULL argument");
+        *out = nullptr;
+        std::unique_ptr<p2p_model> h(new p2p_model);
+        h->m.reset(new Model(e->e.get(), blob, n_floats));
+        *out = h.release();
+    });
+}
+void p2p_model_destroy(p2p_model_t* m) { delete m; }
+
+int p2p_predict(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, float* decode, float* prob) {
+    return guarded([&] {
+        P2P_CHECK(e && m && (n == 0 || (x && decode && prob)), "NULL argument");
+        e->e->predict_host(*m->m, x, n, decode, prob);
+    });
+}
+
+int p2p_predict_device(p2p_engine_t* e, const p2p_model_t* m, const float* x_dev, int n, float* decode_dev,
+                       float* prob_dev, void* stream) {
+    return guarded([&] {
+        P2P_CHECK(e && m && x_dev && decode_dev && prob_dev, "NULL argument");
+        e->e->forward(*m->m, x_dev, n, decode_dev, prob_dev, nullptr, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int p2p_engine_read_tensor(p2p_engine_t* e, const char* name, int n, float* out, int* h, int* w, int* c) {
+    return guarded([&] {
+        P2P_CHECK(e && name, "NULL argument");
+        const int id = e->e->plan.tensor_id(name);
+        const TensorSpec& t = e->e->plan.tensors[id];
+        if (h) *h = t.H;
+        if (w) *w = t.W;
+        if (c) *c = t.C;
+        if (out) e->e->read_tensor(name, n, out);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Generator execution engine: topology ("plan"), activation workspace, TMA tensor maps,
+// weight packing, forward.  Host side of csrc/conv_tc.cuh.
+//
+// Reference graph: pix2pose_model/ae_model.py:175-240 (resnet50) and :70-150 (paper);
+// resnet50_mod.py:40-118, 200-213.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace p2p {
+
+enum Backbone : int { BB_RESNET50 = 0, BB_PAPER = 1 };
+enum Precision : int { PREC_FP16X3 = 0, PREC_FP16 = 1 };
+
+enum LayerKind : int { L_CONV = 0, L_CONVT = 1, L_DENSE = 2, L_BN = 3 };
+struct LayerDef {
+    std::string name;
+    int kind;
+    int shape[4];  // Keras layout; BN: shape[0] = C
+    size_t count() const;   // floats of all tensors of the layer (kernel + bias, or 4*C)
+};
+std::vector<LayerDef> layer_table(int backbone);
+size_t param_count(int backbone);
+int parse_backbone(const char* s);
+
+enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4 };
+
+struct SrcSpec { int tensor, c_begin, c_count; };
+struct WPart { std::string layer, bn; };
+
+struct KWeight { int kh, kw, cin_begin, nvalid; };  // where a k-iteration's 64 K-rows come from
+
+struct ConvSpec {
+    std::string name;
+    int kind = K_CONV, ksize = 1;
+    std::vector<SrcSpec> srcs;
+    std::vector<WPart> parts;
+    int out_tensor = -1, c_off = 0, act = ACT_NONE, res_tensor = -1;
+    // derived by Plan::finalize
+    int H = 0, W = 0, tw = 0, th = 0, nb = 0, phases = 1;
+    int Cin = 0, Cout = 0, Cout_pad = 0, BN = 0;
+    int kstart[5] = {0, 0, 0, 0, 0};
+    int oy_off[4] = {0, 0, 0, 0}, ox_off[4] = {0, 0, 0, 0}, sy = 1, sx = 1;
+    std::vector<int4> kit;
+    std::vector<KWeight> kw;
+    struct MapReq { int tensor, view, climit; };  // view: 0 normal, 1..4 parity (py*2+px+1), 5 dense
+    std::vector<MapReq> maps;
+};
+
+struct TensorSpec { std::string name; int H, W, C; };
+
+enum StepKind : int { S_IM2COL = 0, S_CONV = 1, S_MAXPOOL = 2 };
+struct Step { int kind; int a, b, c, d; };  // CONV: a = conv index; IM2COL: a=out tensor,b=ks,c=pad ; MAXPOOL: a=in,b=out
+
+struct Plan {
+    int backbone;
+    std::vector<TensorSpec> tensors;
+    std::vector<ConvSpec> convs;
+    std::vector<Step> steps;
+    int tensor_id(const std::string& n) const;
+    double flops_per_crop() const;  // 2 * MAC of the contractions (algorithmic, unpadded)
+};
+Plan build_plan(int backbone);
+
+struct ModelConv {
+    DevBuf<__half> packed;  // [KI][NP][Cout_pad][64]
+    DevBuf<float> scale, shift;
+    CUtensorMap mapB;
+};
+
+class Engine;
+
+class Model {
+  public:
+    Model(Engine* eng, const float* blob, size_t n_floats);
+    std::vector<ModelConv> convs;
+    Engine* engine;
+};
+
+class Engine {
+  public:
+    Engine(int backbone, int capacity, int precision);
+    ~Engine();
+    int backbone, cap, np;
+    Plan plan;
+    cudaStream_t stream = nullptr;
+    struct Tensor { DevBuf<__half> buf; long long plane = 0; };
+    std::vector<Tensor> tensors;
+    DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
+    struct ConvRt { DevBuf<int4> kit; CUtensorMap mapA[4]; };
+    std::vector<ConvRt> conv_rt;
+    int num_sms = 148;
+
+    // x_dev -> dec_dev / prob_dev for n <= cap crops; n_active (device int) optionally limits work further.
+    void forward(const Model& m, const float* x_dev, int n, float* dec_dev, float* prob_dev, const int* n_active,
+                 cudaStream_t s);
+    // host in / host out, chunks of `cap`.
+    void predict_host(const Model& m, const float* x, int n, float* dec, float* prob);
+    void read_tensor(const std::string& name, int n, float* out);  // debug: activation (n,H,W,C) as fp32
+    long long launches = 0;  // kernels launched so far (for bench's gpu_launches)
+};
+
+}  // namespace p2p
