@@ -67,6 +67,26 @@ P2P_API int p2p_predict(p2p_engine_t* e, const p2p_model_t* m, const float* x, i
 P2P_API int p2p_predict_device(p2p_engine_t* e, const p2p_model_t* m, const float* x_dev, int n, float* decode_dev,
                        float* prob_dev, void* stream);
 
+/* cv2.solvePnPRansac(obj, img, camK, None, flags=cv2.SOLVEPNP_EPNP, reprojectionError=reproj_err,
+ * iterationsCount=iters, confidence=confidence) followed by cv2.Rodrigues(rvec) (recognition.py:216-223).
+ * obj_pts (n,3) / img_pts (n,2) double host arrays (converted to float32 as OpenCV does), K row-major 3x3.
+ * Outputs: rvec, tvec (EPnP refit on the inliers), R = Rodrigues(rvec), *n_inliers = len(inliers) or -1 when
+ * OpenCV would return inliers=None (no hypothesis with more than 4 inliers) or n < 6 (the reference never
+ * calls with n < 6, recognition.py:214), inlier_mask (n bytes, may be NULL), *iters_run (may be NULL) =
+ * iterations the adaptive RANSAC loop executes. */
+P2P_API int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, const double* K, float reproj_err, int iters,
+                   double confidence, double* rvec, double* tvec, double* R, int* n_inliers, uint8_t* inlier_mask,
+                   int* iters_run);
+
+/* Measurement helper: uploads x (n <= capacity crops, host), then times `iters` device-resident
+ * forwards after `warmup` untimed ones with CUDA events on the engine's stream; *ms_per_iter is
+ * the mean.  Inputs stay in HBM: this is the kernel-only number (bench.py `value`). */
+P2P_API int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,
+                     float* ms_per_iter);
+/* Page-locked host buffers for the end-to-end path (bench.py `e2e`). */
+P2P_API void* p2p_host_alloc(size_t bytes);
+P2P_API void p2p_host_free(void* p);
+
 /* Debug/parity: copy intermediate activation `name` (e.g. "f1", "act3d", "d2_uni") of the last
  * forward as (n,H,W,C) fp32; *h,*w,*c receive the shape. `out` may be NULL to query the shape. */
 P2P_API int p2p_engine_read_tensor(p2p_engine_t* e, const char* name, int n, float* out, int* h, int* w, int* c);

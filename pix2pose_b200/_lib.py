@@ -55,6 +55,11 @@ def lib():
         "p2p_model_destroy": (None, [vp]),
         "p2p_predict": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, c_f, c_f]),
         "p2p_predict_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
+        "p2p_pnp_ransac": (ctypes.c_int, [c_d, c_d, ctypes.c_int, c_d, ctypes.c_float, ctypes.c_int, ctypes.c_double,
+                                          c_d, c_d, c_d, c_i, ctypes.POINTER(ctypes.c_uint8), c_i]),
+        "p2p_time_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_host_alloc": (vp, [ctypes.c_size_t]),
+        "p2p_host_free": (None, [vp]),
         "p2p_engine_read_tensor": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int, c_f, c_i, c_i, c_i]),
     }
     for name, (res, args) in sig.items():
@@ -77,3 +82,18 @@ def fptr(a):
 
 def as_f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def pinned_array(shape, dtype=np.float32):
+    """numpy view over cudaMallocHost memory (freed when the returned array's base is collected)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().p2p_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError("cudaMallocHost(%d) failed" % n)
+    buf = (ctypes.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _pinned_keep[arr.ctypes.data] = p
+    return arr
+
+
+_pinned_keep = {}

@@ -101,6 +101,14 @@ class GeneratorModel:
         _lib.check(_lib.lib().p2p_predict(self.engine.handle, self._model, _lib.fptr(x), n, _lib.fptr(dec), _lib.fptr(prob)))
         return [dec, prob]
 
+    def time_forward(self, x, warmup=3, iters=10):
+        """Device-resident forward time in ms (CUDA events); x: (n<=capacity,128,128,3)."""
+        x = _lib.as_f32(x)
+        ms = ctypes.c_float()
+        _lib.check(_lib.lib().p2p_time_forward(self.engine.handle, self._model, _lib.fptr(x), x.shape[0], warmup, iters,
+                                               ctypes.byref(ms)))
+        return ms.value
+
     def _release(self):
         if self._model is not None:
             _lib.lib().p2p_model_destroy(self._model)

@@ -2,6 +2,7 @@
 #include "../../include/pix2pose_b200.h"
 
 #include "engine.cuh"
+#include "pnp_ransac.cuh"
 
 using namespace p2p;
 
@@ -62,6 +63,59 @@ int p2p_predict_device(p2p_engine_t* e, const p2p_model_t* m, const float* x_dev
         P2P_CHECK(e && m && x_dev && decode_dev && prob_dev, "NULL argument");
         e->e->forward(*m->m, x_dev, n, decode_dev, prob_dev, nullptr, static_cast<cudaStream_t>(stream));
     });
+}
+
+static PnpSolver& default_pnp() {
+    static std::unique_ptr<PnpSolver> s;
+    if (!s) s.reset(new PnpSolver());
+    return *s;
+}
+
+int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, const double* K, float reproj_err, int iters,
+                   double confidence, double* rvec, double* tvec, double* R, int* n_inliers, uint8_t* inlier_mask,
+                   int* iters_run) {
+    return guarded([&] {
+        P2P_CHECK(obj_pts && img_pts && K && rvec && tvec && R && n_inliers, "NULL argument");
+        PnpResult r;
+        default_pnp().solve_host(obj_pts, img_pts, n, K, reproj_err, iters, confidence, &r, inlier_mask);
+        for (int i = 0; i < 3; ++i) { rvec[i] = r.rvec[i]; tvec[i] = r.tvec[i]; }
+        for (int i = 0; i < 9; ++i) R[i] = r.R[i];
+        *n_inliers = r.n_inliers;
+        if (iters_run) *iters_run = r.iters_run;
+    });
+}
+
+int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,
+                     float* ms_per_iter) {
+    return guarded([&] {
+        P2P_CHECK(e && m && x && ms_per_iter && iters > 0 && warmup >= 0, "bad argument");
+        Engine& E = *e->e;
+        P2P_CHECK(n >= 1 && n <= E.cap, "n=%d outside [1,%d]", n, E.cap);
+        P2P_CUDA(cudaMemcpyAsync(E.x.p, x, static_cast<size_t>(n) * 128 * 128 * 3 * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+        for (int i = 0; i < warmup; ++i) E.forward(*m->m, E.x.p, n, E.dec.p, E.prob.p, nullptr, E.stream);
+        cudaEvent_t a, b;
+        P2P_CUDA(cudaEventCreate(&a));
+        P2P_CUDA(cudaEventCreate(&b));
+        P2P_CUDA(cudaStreamSynchronize(E.stream));
+        P2P_CUDA(cudaEventRecord(a, E.stream));
+        for (int i = 0; i < iters; ++i) E.forward(*m->m, E.x.p, n, E.dec.p, E.prob.p, nullptr, E.stream);
+        P2P_CUDA(cudaEventRecord(b, E.stream));
+        P2P_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        P2P_CUDA(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        *ms_per_iter = ms / iters;
+    });
+}
+
+void* p2p_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void p2p_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int p2p_engine_read_tensor(p2p_engine_t* e, const char* name, int n, float* out, int* h, int* w, int* c) {

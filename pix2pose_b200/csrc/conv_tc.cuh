@@ -60,7 +60,13 @@ struct ConvCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    // fp16x3 keeps THREE accumulators in TMEM: two for the hi*hi products (even / odd k-steps) and one
+    // for the 2^-11-times-smaller cross terms.  The tensor core rounds the fp32 accumulator toward zero
+    // after every MMA; splitting the chains divides that bias (measured: resnet50 decode max error
+    // 1.0e-3 with one accumulator).  The epilogue adds the three.
+    static constexpr int NACC = NP == 2 ? 3 : 1;
+    static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;  // TMEM columns between accumulators
+    static constexpr uint32_t TMEM_COLS = NACC * ACC_STRIDE <= 32 ? 32 : (NACC * ACC_STRIDE <= 64 ? 64 : (NACC * ACC_STRIDE <= 128 ? 128 : (NACC * ACC_STRIDE <= 256 ? 256 : 512)));
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -155,12 +161,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                 for (int kk = 0; kk < 4; ++kk) {
                     const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
                     const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                    umma_f16(tmem_base, a_hi, b_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                     if (NP == 2) {
+                        const int g = it * 4 + kk;  // k16 step: even -> accumulator 0, odd -> accumulator 1
+                        umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
                         const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
                         const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                        umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
-                        umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+                        umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
+                        umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_hi, b_lo, idesc, 1u);
+                    } else {
+                        umma_f16(tmem_base, a_hi, b_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
@@ -186,6 +195,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             uint32_t v[16];
             tmem_ld_32x16(taddr, v);
             tmem_ld_wait();
+            if (Cfg::NACC == 3) {
+                uint32_t v1[16], v2[16];
+                tmem_ld_32x16(taddr + Cfg::ACC_STRIDE, v1);
+                tmem_ld_32x16(taddr + 2 * Cfg::ACC_STRIDE, v2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(v1[j])) + __uint_as_float(v2[j]));
+            }
             if (valid) {
                 float* d = p.out_dec + pix * 3;
 #pragma unroll
@@ -201,6 +219,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + ch * 32, v);
                 tmem_ld_wait();
+                if (Cfg::NACC == 3) {
+                    uint32_t v1[32];
+                    tmem_ld_32x32(taddr + Cfg::ACC_STRIDE + ch * 32, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+                    tmem_ld_32x32(taddr + 2 * Cfg::ACC_STRIDE + ch * 32, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+                }
                 const int c0 = nt0 + ch * 32;
                 if (valid && c0 < p.Cout) {
                     __half* o_hi = p.out_hi + pix * p.Ctot + p.c_off + c0;

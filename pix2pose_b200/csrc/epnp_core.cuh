@@ -197,16 +197,85 @@ P2P_HD inline bool qr_solve_6x4(double* A, double* b, double* x) {
     return true;
 }
 
+// Left singular vectors of a 3x3 matrix exactly as OpenCV's JacobiSVDImpl_ (modules/core/src/lapack.cpp)
+// produces them for cvSVD(A, W, Ut, 0, CV_SVD_U_T): one-sided Jacobi on the ROWS of A^T with its
+// rotation formulas, descending sort, rows normalised.  EPnP's control points are c0 + k*u_i, so the
+// SIGN convention of u_i changes the (noisy-data) solution at the 1e-3 level: it must be OpenCV's.
+// ut: rows = singular vectors, w: singular values.
+P2P_HD inline void cv_svd3_ut(const double* A, double* ut, double* w) {
+    const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
+    double At[9], W[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) At[i * 3 + j] = A[j * 3 + i];
+    for (int i = 0; i < 3; ++i) {
+        double sd = 0;
+        for (int k = 0; k < 3; ++k) sd += At[i * 3 + k] * At[i * 3 + k];
+        W[i] = sd;
+    }
+    for (int iter = 0; iter < 30; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < 2; ++i)
+            for (int j = i + 1; j < 3; ++j) {
+                double* Ai = At + i * 3;
+                double* Aj = At + j * 3;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < 3; ++k) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = hypot(p, beta);
+                double c, sn;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    sn = sqrt(delta / gamma);
+                    c = p / (gamma * sn * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    sn = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const double t0 = c * Ai[k] + sn * Aj[k];
+                    const double t1 = -sn * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < 3; ++i) {
+        double sd = 0;
+        for (int k = 0; k < 3; ++k) sd += At[i * 3 + k] * At[i * 3 + k];
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < 2; ++i) {
+        int j = i;
+        for (int k = i + 1; k < 3; ++k)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+            for (int k = 0; k < 3; ++k) { const double t = At[i * 3 + k]; At[i * 3 + k] = At[j * 3 + k]; At[j * 3 + k] = t; }
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        w[i] = W[i];
+        // (OpenCV regenerates the vector from a fixed-seed RNG when W[i] <= DBL_MIN; such exactly
+        //  degenerate point sets -- collinear / identical points -- are left as a zero vector here.)
+        const double sc = W[i] > minval ? 1.0 / W[i] : 0.0;
+        for (int k = 0; k < 3; ++k) ut[i * 3 + k] = At[i * 3 + k] * sc;
+    }
+}
+
 // ---- control points (epnp.cpp choose_control_points) from the centroid and the 3x3 scatter
 // PW0^T PW0 of the n reference points.
 P2P_HD inline void choose_control_points(const double* centroid, const double* scatter, int n, double cws[4][3]) {
-    double S[9], Vt[9], w[3];
-    for (int i = 0; i < 9; ++i) S[i] = scatter[i];
-    jacobi_eig_sym<3>(S, Vt, w);
+    double Ut[9], w[3];
+    cv_svd3_ut(scatter, Ut, w);
     for (int j = 0; j < 3; ++j) cws[0][j] = centroid[j];
     for (int i = 1; i < 4; ++i) {
-        const double k = sqrt(fmax(w[i - 1], 0.0) / n);
-        for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * Vt[3 * (i - 1) + j];
+        const double k = sqrt(w[i - 1] / n);
+        for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * Ut[3 * (i - 1) + j];
     }
 }
 

@@ -1,0 +1,410 @@
+// Batched EPnP-RANSAC kernels.  See pnp_ransac.cuh for the contract and epnp_core.cuh for the math.
+#include "pnp_ransac.cuh"
+
+#include <algorithm>
+#include <vector>
+
+#include "epnp_core.cuh"
+
+namespace p2p {
+
+namespace {
+
+constexpr int kHypThreads = 128;
+constexpr int kScoreWarps = 8;
+constexpr int kRefitThreads = 256;
+
+// cv::projectPoints (no distortion) + PnPRansacCallback::computeError for one correspondence:
+// projection in double, stored as float32, squared error accumulated in float32 without FMA.
+__device__ __forceinline__ float reproj_err_f32(const double* R, const double* t, const float* o, const float* ip,
+                                                double fu, double fv, double uc, double vc) {
+    const double X = o[0], Y = o[1], Z = o[2];
+    double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+    double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+    double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    z = z != 0.0 ? 1.0 / z : 1.0;
+    x *= z;
+    y *= z;
+    const float u = static_cast<float>(x * fu + uc), v = static_cast<float>(y * fv + vc);
+    const float dx = __fsub_rn(ip[0], u), dy = __fsub_rn(ip[1], v);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// ---- (1) hypotheses: RNG replay by thread 0, then one 5-point EPnP per thread
+__global__ void __launch_bounds__(kHypThreads) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
+                                                                 const float* __restrict__ obj, const float* __restrict__ img,
+                                                                 double* __restrict__ hyp, int iters) {
+    extern __shared__ int s_idx[];
+    const PnpProblem pr = probs[blockIdx.x];
+    if (pr.n < 6) return;
+    if (threadIdx.x == 0) {
+        CvRng rng;
+        for (int i = 0; i < iters; ++i) ransac_subset5(rng, pr.n, s_idx + 5 * i);
+    }
+    __syncthreads();
+    const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
+    const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
+    for (int h = threadIdx.x; h < iters; h += blockDim.x) {
+        double pws[15], us[10];
+        for (int j = 0; j < 5; ++j) {
+            const long long g = pr.offset + s_idx[5 * h + j];
+            for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(obj[g * 3 + k]);
+            // cv::undistortPoints on CV_32FC2 (no distortion): normalised in double, stored as float32;
+            // epnp::init_points then maps back to pixels in double.
+            const float xn = static_cast<float>((static_cast<double>(img[g * 2]) - pr.uc) * ifx);
+            const float yn = static_cast<float>((static_cast<double>(img[g * 2 + 1]) - pr.vc) * ify);
+            us[2 * j] = static_cast<double>(xn) * pr.fu + pr.uc;
+            us[2 * j + 1] = static_cast<double>(yn) * pr.fv + pr.vc;
+        }
+        double R[3][3], t[3], rv[3];
+        epnp::solve_small<5>(pws, us, 5, cam, R, t);
+        epnp::rodrigues_to_vec(R, rv);   // the RANSAC model is (rvec, tvec) ...
+        epnp::rodrigues_to_mat(rv, R);   // ... and projectPoints turns rvec back into a matrix
+        double* o = hyp + (static_cast<long long>(blockIdx.x) * iters + h) * 12;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) o[i * 3 + j] = R[i][j];
+        o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
+    }
+}
+
+// ---- (2) scoring: one warp per hypothesis over all correspondences of its problem
+__global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const PnpProblem* __restrict__ probs,
+                                                                       const float* __restrict__ obj,
+                                                                       const float* __restrict__ img,
+                                                                       const double* __restrict__ hyp, int* __restrict__ counts,
+                                                                       int iters, float thr2) {
+    const PnpProblem pr = probs[blockIdx.y];
+    const int h = blockIdx.x * kScoreWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pr.n < 6 || h >= iters) return;
+    const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
+    double R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = m[i];
+    t[0] = m[9]; t[1] = m[10]; t[2] = m[11];
+    const float* o = obj + pr.offset * 3;
+    const float* ip = img + pr.offset * 2;
+    int cnt = 0;
+    for (int i = lane; i < pr.n; i += 32) {
+        const float e = reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc);
+        cnt += (e <= thr2) ? 1 : 0;  // NaN compares false, as in findInliers
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (lane == 0) counts[blockIdx.y * iters + h] = cnt;
+}
+
+// ---- (3) replay of RANSACPointSetRegistrator::run's accept / adaptive-termination rule + inlier mask
+__global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __restrict__ probs, const float* __restrict__ obj,
+                                                            const float* __restrict__ img, const double* __restrict__ hyp,
+                                                            const int* __restrict__ counts, int* __restrict__ best,
+                                                            uint8_t* __restrict__ mask, PnpResult* __restrict__ res,
+                                                            int iters, float thr2, double confidence) {
+    __shared__ int s_best;
+    const PnpProblem pr = probs[blockIdx.x];
+    PnpResult* out = res + blockIdx.x;
+    if (pr.n < 6) {
+        if (threadIdx.x == 0) {
+            out->status = -1; out->n_inliers = -1; out->best_iter = -1; out->iters_run = 0;
+            best[2 * blockIdx.x] = -1; best[2 * blockIdx.x + 1] = 0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        int max_good = 0, niters = iters > 1 ? iters : 1, b = -1, it = 0;
+        for (; it < niters; ++it) {
+            const int c = counts[blockIdx.x * iters + it];
+            if (c > (max_good > 4 ? max_good : 4)) {  // goodCount > MAX(maxGoodCount, modelPoints-1)
+                b = it;
+                max_good = c;
+                niters = ransac_update_num_iters(confidence, static_cast<double>(pr.n - c) / pr.n, 5, niters);
+            }
+        }
+        s_best = b;
+        best[2 * blockIdx.x] = b;
+        best[2 * blockIdx.x + 1] = max_good;
+        out->best_iter = b;
+        out->iters_run = it;
+        out->n_inliers = b >= 0 ? max_good : -1;
+        out->status = b >= 0 ? 1 : 0;
+    }
+    __syncthreads();
+    const int b = s_best;
+    uint8_t* mk = mask + pr.offset;
+    if (b < 0) {
+        for (int i = threadIdx.x; i < pr.n; i += blockDim.x) mk[i] = 0;
+        return;
+    }
+    const double* m = hyp + (static_cast<long long>(blockIdx.x) * iters + b) * 12;
+    double R[9], t[3];
+    for (int i = 0; i < 9; ++i) R[i] = m[i];
+    t[0] = m[9]; t[1] = m[10]; t[2] = m[11];
+    const float* o = obj + pr.offset * 3;
+    const float* ip = img + pr.offset * 2;
+    for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
+        mk[i] = reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2 ? 1 : 0;
+}
+
+// ---- (4) EPnP on all inliers (double), one CTA per problem
+template <int NV>
+__device__ __forceinline__ void block_reduce(double* v, double* s_red, double* s_out) {
+    // v[NV] per thread -> s_out[NV] block sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) s_red[warp * NV + k] = x;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NV; k += blockDim.x) {
+        double x = 0;
+        for (int w = 0; w < nw; ++w) x += s_red[w * NV + k];
+        s_out[k] = x;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRefitThreads) epnp_refit_kernel(const PnpProblem* __restrict__ probs,
+                                                                   const float* __restrict__ obj, const float* __restrict__ img,
+                                                                   const uint8_t* __restrict__ mask, PnpResult* __restrict__ res) {
+    __shared__ double s_red[(kRefitThreads / 32) * 52];
+    __shared__ double s_sum[52];
+    __shared__ double s_cws[4][3], s_ci[9], s_ccs[3][4][3], s_R[3][3][3], s_t[3][3];
+    __shared__ int s_first;
+    const PnpProblem pr = probs[blockIdx.x];
+    PnpResult* out = res + blockIdx.x;
+    if (pr.n < 6 || out->status != 1) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 3; ++i) { out->rvec[i] = 0; out->tvec[i] = 0; }
+            for (int i = 0; i < 9; ++i) out->R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        }
+        return;
+    }
+    const float* o = obj + pr.offset * 3;
+    const float* ip = img + pr.offset * 2;
+    const uint8_t* mk = mask + pr.offset;
+    const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+
+    // pass A: centroid, count, index of the first inlier (solve_for_sign looks at point 0)
+    {
+        double v[4] = {0, 0, 0, 0};
+        int first = 0x7fffffff;
+        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
+            if (mk[i]) {
+                v[0] += o[3 * i]; v[1] += o[3 * i + 1]; v[2] += o[3 * i + 2]; v[3] += 1.0;
+                first = min(first, i);
+            }
+        atomicMin(&s_first, first);
+        block_reduce<4>(v, s_red, s_sum);
+    }
+    const int m = static_cast<int>(s_sum[3] + 0.5);
+    const double c0[3] = {s_sum[0] / m, s_sum[1] / m, s_sum[2] / m};
+    __syncthreads();
+    // pass B: scatter matrix PW0^T PW0
+    {
+        double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
+            if (mk[i]) {
+                const double d[3] = {o[3 * i] - c0[0], o[3 * i + 1] - c0[1], o[3 * i + 2] - c0[2]};
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) v[a * 3 + b] += d[a] * d[b];
+            }
+        block_reduce<9>(v, s_red, s_sum);
+    }
+    if (threadIdx.x == 0) {
+        double sc[9];
+        for (int i = 0; i < 9; ++i) sc[i] = s_sum[i];
+        epnp::choose_control_points(c0, sc, m, s_cws);
+        epnp::control_inverse(s_cws, s_ci);
+    }
+    __syncthreads();
+    // pass C: M^T M in its structured form (10 alpha pairs x {1, uc-u, vc-v, (uc-u)^2+(vc-v)^2}) and
+    //         T_j = sum alpha_j (pw - c0) for the R|t correlation
+    {
+        double v[52];
+#pragma unroll
+        for (int k = 0; k < 52; ++k) v[k] = 0;
+        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
+            if (mk[i]) {
+                const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
+                double a[4];
+                epnp::barycentric(s_ci, s_cws, p, a);
+                const double du = pr.uc - static_cast<double>(ip[2 * i]), dv = pr.vc - static_cast<double>(ip[2 * i + 1]);
+                const double q = du * du + dv * dv;
+                int k = 0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = x; y < 4; ++y) {
+                        const double aa = a[x] * a[y];
+                        v[k] += aa; v[10 + k] += aa * du; v[20 + k] += aa * dv; v[30 + k] += aa * q;
+                        ++k;
+                    }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[40 + j * 3 + c] += a[j] * (p[c] - c0[c]);
+            }
+        block_reduce<52>(v, s_red, s_sum);
+    }
+    if (threadIdx.x == 0) {
+        double mtm[144], ut[144], betas[3][4];
+        int k = 0;
+        for (int x = 0; x < 4; ++x)
+            for (int y = x; y < 4; ++y) {
+                const double S = s_sum[k], Su = s_sum[10 + k], Sv = s_sum[20 + k], Sq = s_sum[30 + k];
+                const double blk[9] = {pr.fu * pr.fu * S, 0, pr.fu * Su, 0, pr.fv * pr.fv * S, pr.fv * Sv, pr.fu * Su, pr.fv * Sv, Sq};
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        mtm[(3 * x + r) * 12 + 3 * y + c] = blk[r * 3 + c];
+                        mtm[(3 * y + c) * 12 + 3 * x + r] = blk[r * 3 + c];
+                    }
+                ++k;
+            }
+        epnp::solve_betas(mtm, s_cws, ut, betas);
+        // sign reference: camera-frame z of the first inlier (epnp.cpp solve_for_sign uses pcs[2])
+        const int f = s_first;
+        const double pf[3] = {o[3 * f], o[3 * f + 1], o[3 * f + 2]};
+        double af[4];
+        epnp::barycentric(s_ci, s_cws, pf, af);
+        for (int c = 0; c < 3; ++c) {
+            double ccs[4][3], pc[3];
+            epnp::compute_ccs(betas[c], ut, ccs);
+            epnp::camera_point(af, ccs, pc);
+            const double sg = pc[2] < 0.0 ? -1.0 : 1.0;
+            // pc0 = sum_j mean(alpha_j) ccs_j and ABt = sum_j ccs_j T_j^T - m pc0 (pw0 - c0)^T; alphas are
+            // affine in pw, so with S_j = sum alpha_j:  pc0 = sum_j (S_j/m) ccs_j ; pw0 = c0 exactly.
+            double pc0[3] = {0, 0, 0}, abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < 4; ++j)
+                for (int r = 0; r < 3; ++r) {
+                    ccs[j][r] *= sg;
+                    s_ccs[c][j][r] = ccs[j][r];
+                }
+            // S_j = sum_i alpha_ij = sum over pairs containing j ... alpha sums to 1 per point, so
+            // sum_i alpha_ij = sum_y sum_i alpha_ij alpha_iy = row sums of the pair table.
+            double Srow[4] = {0, 0, 0, 0};
+            {
+                int kk = 0;
+                for (int x = 0; x < 4; ++x)
+                    for (int y = x; y < 4; ++y) {
+                        Srow[x] += s_sum[kk];
+                        if (y != x) Srow[y] += s_sum[kk];
+                        ++kk;
+                    }
+            }
+            for (int j = 0; j < 4; ++j)
+                for (int r = 0; r < 3; ++r) pc0[r] += Srow[j] / m * ccs[j][r];
+            for (int j = 0; j < 4; ++j)
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s_sum[40 + j * 3 + q];
+            // subtract pc0 (x) sum(pw - c0); the latter is ~0 (rounding only) but kept for fidelity
+            double dsum[3] = {0, 0, 0};
+            for (int j = 0; j < 4; ++j)
+                for (int q = 0; q < 3; ++q) dsum[q] += s_sum[40 + j * 3 + q];
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * dsum[q];
+            double Rk[3][3], tk[3];
+            epnp::rt_from_correlation(abt, pc0, c0, Rk, tk);
+            for (int r = 0; r < 3; ++r) {
+                s_t[c][r] = tk[r];
+                for (int q = 0; q < 3; ++q) s_R[c][r][q] = Rk[r][q];
+            }
+        }
+    }
+    __syncthreads();
+    // pass E: mean reprojection distance of each of the three candidates
+    {
+        double v[3] = {0, 0, 0};
+        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
+            if (mk[i]) {
+                const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
+                const double u = ip[2 * i], vv = ip[2 * i + 1];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] += epnp::reproj_dist(s_R[c], s_t[c], p, u, vv, cam);
+            }
+        block_reduce<3>(v, s_red, s_sum);
+    }
+    if (threadIdx.x == 0) {
+        int N = 0;
+        if (s_sum[1] < s_sum[0]) N = 1;
+        if (s_sum[2] < s_sum[N]) N = 2;
+        double rv[3], Rf[3][3];
+        epnp::rodrigues_to_vec(s_R[N], rv);
+        epnp::rodrigues_to_mat(rv, Rf);
+        for (int i = 0; i < 3; ++i) {
+            out->rvec[i] = rv[i];
+            out->tvec[i] = s_t[N][i];
+            for (int j = 0; j < 3; ++j) out->R[i * 3 + j] = Rf[i][j];
+        }
+    }
+}
+
+}  // namespace
+
+PnpSolver::PnpSolver() {
+    require_device();
+    P2P_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+}
+PnpSolver::~PnpSolver() {
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void PnpSolver::ensure(int n_problems, int iters) {
+    if (n_problems > cap_problems_ || iters > cap_iters_) {
+        cap_problems_ = std::max(n_problems, cap_problems_);
+        cap_iters_ = std::max(iters, cap_iters_);
+        hyp_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_ * 12);
+        counts_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_);
+        best_.alloc(static_cast<size_t>(cap_problems_) * 2);
+    }
+}
+
+void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, const float* obj_dev, const float* img_dev,
+                            uint8_t* mask_dev, PnpResult* results_dev, float reproj_err, int iters, double confidence,
+                            cudaStream_t s) {
+    if (n_problems <= 0) return;
+    P2P_CHECK(iters >= 1 && iters <= 4096, "iterationsCount %d outside [1,4096]", iters);
+    P2P_CHECK(confidence > 0 && confidence < 1, "confidence must be in (0,1)");
+    ensure(n_problems, iters);
+    const float thr2 = static_cast<float>(static_cast<double>(reproj_err) * static_cast<double>(reproj_err));
+    ransac_hyp_kernel<<<n_problems, kHypThreads, iters * 5 * sizeof(int), s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    P2P_CUDA(cudaGetLastError());
+    dim3 g((iters + kScoreWarps - 1) / kScoreWarps, n_problems);
+    ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, thr2);
+    P2P_CUDA(cudaGetLastError());
+    ransac_select_kernel<<<n_problems, 256, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, best_.p, mask_dev,
+                                                    results_dev, iters, thr2, confidence);
+    P2P_CUDA(cudaGetLastError());
+    epnp_refit_kernel<<<n_problems, kRefitThreads, 0, s>>>(problems_dev, obj_dev, img_dev, mask_dev, results_dev);
+    P2P_CUDA(cudaGetLastError());
+    launches += 4;
+}
+
+void PnpSolver::solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,
+                           double confidence, PnpResult* out, uint8_t* mask_out) {
+    P2P_CHECK(obj && img && K9 && out, "NULL argument");
+    P2P_CHECK(n >= 0, "negative point count");
+    std::vector<float> o(static_cast<size_t>(n) * 3), ip(static_cast<size_t>(n) * 2);
+    for (size_t i = 0; i < o.size(); ++i) o[i] = static_cast<float>(obj[i]);   // Mat::convertTo(CV_32F)
+    for (size_t i = 0; i < ip.size(); ++i) ip[i] = static_cast<float>(img[i]);
+    PnpProblem pr;
+    pr.offset = 0; pr.n = n; pr.pad = 0;
+    pr.fu = K9[0]; pr.fv = K9[4]; pr.uc = K9[2]; pr.vc = K9[5];
+    h_obj_.upload(o.data(), o.size(), stream_);
+    h_img_.upload(ip.data(), ip.size(), stream_);
+    if (h_mask_.n < static_cast<size_t>(n) + 1) h_mask_.alloc(static_cast<size_t>(n) + 1);
+    h_prob_.upload(&pr, 1, stream_);
+    if (h_res_.n < 1) h_res_.alloc(1);
+    solve_batch(h_prob_.p, 1, h_obj_.p, h_img_.p, h_mask_.p, h_res_.p, reproj_err, iters, confidence, stream_);
+    P2P_CUDA(cudaMemcpyAsync(out, h_res_.p, sizeof(PnpResult), cudaMemcpyDeviceToHost, stream_));
+    if (mask_out && n > 0) P2P_CUDA(cudaMemcpyAsync(mask_out, h_mask_.p, n, cudaMemcpyDeviceToHost, stream_));
+    P2P_CUDA(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace p2p

@@ -1,0 +1,63 @@
+// Batched PnP-RANSAC (EPnP minimal solver) on the GPU -- replaces the CPU call
+//   cv2.solvePnPRansac(obj, img, camK, None, flags=SOLVEPNP_EPNP, reprojectionError=5, iterationsCount=100)
+// of pix2pose_model/recognition.py:216-217 followed by cv2.Rodrigues (:223).
+//
+// Semantics follow OpenCV's solvePnPRansac / RANSACPointSetRegistrator (third-party, not vendored in
+// the reference; see epnp_core.cuh): float32 correspondences, 5-point subsets drawn with OpenCV's
+// fixed-seed RNG, squared float32 reprojection error <= thr^2, "accept if goodCount > max(best, 4)",
+// adaptive iteration count at the given confidence, final EPnP on all inliers in double.
+// All `iters` hypotheses are evaluated in parallel; the sequential accept/terminate rule is then
+// replayed in iteration order, which selects the same hypothesis OpenCV would have stopped at.
+//
+// Kernels: (1) one thread per hypothesis: 5-point EPnP (fp64); (2) one warp per hypothesis: score
+// all correspondences, warp-shuffle reduction of the inlier count; (3) replay + inlier mask;
+// (4) one CTA per problem: EPnP refit on the inliers (block reductions of the 12x12 normal matrix).
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace p2p {
+
+struct PnpProblem {
+    long long offset;  // first correspondence of this problem in the pools
+    int n;             // number of correspondences (problems with n < 6 are skipped: status -1)
+    int pad;
+    double fu, fv, uc, vc;
+};
+
+struct PnpResult {
+    double rvec[3], tvec[3], R[9];  // R = Rodrigues(rvec), as recognition.py:221-223 builds it
+    int n_inliers;                  // len(inliers) or -1 when RANSAC found no model / n < 6
+    int best_iter;                  // iteration whose hypothesis won
+    int iters_run;                  // iterations OpenCV's adaptive loop would have executed
+    int status;                     // 1 ok, 0 no consensus, -1 too few points
+};
+
+class PnpSolver {
+  public:
+    PnpSolver();
+    ~PnpSolver();
+    // Device-side batch: pools obj (total x 3 f32), img (total x 2 f32), mask (total u8, written).
+    void solve_batch(const PnpProblem* problems_dev, int n_problems, const float* obj_dev, const float* img_dev,
+                     uint8_t* mask_dev, PnpResult* results_dev, float reproj_err, int iters, double confidence,
+                     cudaStream_t s);
+    // Host convenience: one problem, double inputs converted to float32 like OpenCV does.
+    void solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,
+                    double confidence, PnpResult* out, uint8_t* mask_out);
+    long long launches = 0;
+
+  private:
+    void ensure(int n_problems, int iters);
+    DevBuf<double> hyp_;   // [problems][iters][12]
+    DevBuf<int> counts_;   // [problems][iters]
+    DevBuf<int> best_;     // [problems][2]
+    int cap_problems_ = 0, cap_iters_ = 0;
+    cudaStream_t stream_ = nullptr;
+    DevBuf<float> h_obj_, h_img_;
+    DevBuf<uint8_t> h_mask_;
+    DevBuf<PnpProblem> h_prob_;
+    DevBuf<PnpResult> h_res_;
+};
+
+}  // namespace p2p

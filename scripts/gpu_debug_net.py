@@ -57,7 +57,9 @@ def timing(bb="resnet50", prec="fp16x3", n=64, reps=5):
     for _ in range(reps):
         m.predict(x)
     dt = (time.time() - t) / reps
-    print("[timing %s/%s] n=%d  %.2f ms/batch (host in/out)  %.0f crops/s" % (bb, prec, n, dt * 1e3, n / dt), flush=True)
+    ms = m.time_forward(x, 3, 10)
+    print("[timing %s/%s] n=%d  %.2f ms/batch (host in/out)  %.0f crops/s | device %.3f ms  %.0f crops/s" % (
+        bb, prec, n, dt * 1e3, n / dt, ms, n / ms * 1e3), flush=True)
 
 
 if __name__ == "__main__" and os.environ.get("P2P_TIMING"):
