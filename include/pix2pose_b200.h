@@ -78,6 +78,54 @@ P2P_API int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, 
                    double confidence, double* rvec, double* tvec, double* R, int* n_inliers, uint8_t* inlier_mask,
                    int* iters_run);
 
+/* ---- batched est_pose (recognition.py:70-193) ------------------------------------------------
+ * One p2p_det_t per est_pose(rgb, bbox) call.  The host fills everything except pool_off / cap_px
+ * (pix2pose_b200/recognition.py does the get_boxes arithmetic exactly as the reference). */
+typedef struct p2p_det {
+    int frame;           /* index into the frame batch                                              */
+    int skip;            /* 1: stage-1 size guard (recognition.py:78-79) tripped                    */
+    int bbox[4];         /* roi [v0,u0,v1,u1]                                                       */
+    int box1[12];        /* get_boxes(bbox, H, W) -> v1_ori,v2_ori,u1_ori,u2_ori,v1,v2,u1,u2,vv1,vv2,uu1,uu2 */
+    double fu, fv, uc, vc; /* self.camK                                                             */
+    double scale[3], ct[3]; /* obj_param                                                            */
+    long long pool_off;  /* internal */
+    int cap_px, pad;     /* internal */
+} p2p_det_t;
+
+typedef struct p2p_pose {
+    double R[9], t[3];   /* rot_pred, tra_pred (model units, mm)                                     */
+    double frac_inlier;  /* max_inlier / n_init_mask, or -1                                          */
+    int status;          /* 1 ok; 0 the reference returns the -1 sentinels; -2 stage-1 size guard    */
+    int n_inliers, best_cand, n_cand;
+    int bbox_t[4];       /* [v1,v2,u1,u2] as returned by the reference                               */
+    int best_box[12];    /* box of the winning candidate (where img_pred / valid_mask live)          */
+    int n_init;          /* n_init_mask                                                              */
+    int mask_all_true;   /* valid_mask == -1 case (recognition.py:219)                               */
+    int cand_base, pad;
+} p2p_pose_t;
+
+typedef struct p2p_pipeline p2p_pipeline_t;
+P2P_API int p2p_pipeline_create(p2p_engine_t* e, int max_dets, int n_thresholds, p2p_pipeline_t** out);
+P2P_API void p2p_pipeline_destroy(p2p_pipeline_t* p);
+/* frames: (F,H,W,3) uint8 host memory (copied to the device inside the call); dets[n]; th_outlier
+ * [n_thresholds]; PnP parameters as hard-coded by recognition.py:216-217 are (5, 100, 0.99). */
+P2P_API int p2p_pipeline_run(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames, int F, int H, int W,
+                     const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                     int iters, double confidence, p2p_pose_t* out);
+/* Same with frames already on the device. */
+P2P_API int p2p_pipeline_run_device(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames_dev, int F, int H, int W,
+                            const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                            int iters, double confidence, p2p_pose_t* out);
+/* After a run: winner's uint8 XYZ crop (h,w,3) and valid mask (h,w), h = best_box[5]-best_box[4], w = [7]-[6]. */
+P2P_API int p2p_pipeline_fetch_crop(p2p_pipeline_t* p, int det, const p2p_pose_t* rec, uint8_t* xyz, uint8_t* mask);
+/* Raw (128,128,3) network output: stage 1 (index = detection) or stage 2 (index = cand_base + k). */
+P2P_API int p2p_pipeline_fetch_decode(p2p_pipeline_t* p, int stage, int index, float* out);
+/* Debug / parity: raw float buffers of the last run. what: 1 dec1, 2 dec2, 3 x1, 4 x2 ((128,128,3)), 5 prob1, 6 prob2 ((128,128)). */
+P2P_API int p2p_pipeline_fetch_buffer(p2p_pipeline_t* p, int what, int index, float* out);
+/* Test hook: the NEXT run replaces the network outputs of `stage` (1|2) by these host arrays (planted-pose parity tests). */
+P2P_API int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decode, const float* prob, int n);
+P2P_API long long p2p_pipeline_launch_count(const p2p_pipeline_t* p);
+
 /* Measurement helper: uploads x (n <= capacity crops, host), then times `iters` device-resident
  * forwards after `warmup` untimed ones with CUDA events on the engine's stream; *ms_per_iter is
  * the mean.  Inputs stay in HBM: this is the kernel-only number (bench.py `value`). */

@@ -57,6 +57,17 @@ def lib():
         "p2p_predict_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
         "p2p_pnp_ransac": (ctypes.c_int, [c_d, c_d, ctypes.c_int, c_d, ctypes.c_float, ctypes.c_int, ctypes.c_double,
                                           c_d, c_d, c_d, c_i, ctypes.POINTER(ctypes.c_uint8), c_i]),
+        "p2p_pipeline_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+        "p2p_pipeline_destroy": (None, [vp]),
+        "p2p_pipeline_run": (ctypes.c_int, [vp, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                            ctypes.c_int, c_d, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
+        "p2p_pipeline_run_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                                   ctypes.c_int, c_d, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
+        "p2p_pipeline_fetch_crop": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8)]),
+        "p2p_pipeline_fetch_decode": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_pipeline_fetch_buffer": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_pipeline_debug_override": (ctypes.c_int, [vp, ctypes.c_int, c_f, c_f, ctypes.c_int]),
+        "p2p_pipeline_launch_count": (ctypes.c_longlong, [vp]),
         "p2p_time_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]),
         "p2p_host_alloc": (vp, [ctypes.c_size_t]),
         "p2p_host_free": (None, [vp]),

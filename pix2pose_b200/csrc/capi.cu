@@ -3,11 +3,15 @@
 
 #include "engine.cuh"
 #include "pnp_ransac.cuh"
+#include "pipeline.cuh"
 
 using namespace p2p;
 
 struct p2p_engine { std::unique_ptr<Engine> e; };
 struct p2p_model { std::unique_ptr<Model> m; };
+struct p2p_pipeline { std::unique_ptr<Pipeline> p; };
+static_assert(sizeof(p2p_det_t) == sizeof(DetIn), "p2p_det_t must mirror DetIn");
+static_assert(sizeof(p2p_pose_t) == sizeof(PoseRecord), "p2p_pose_t must mirror PoseRecord");
 
 extern "C" {
 
@@ -84,6 +88,65 @@ int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, const do
         if (iters_run) *iters_run = r.iters_run;
     });
 }
+
+int p2p_pipeline_create(p2p_engine_t* e, int max_dets, int n_thresholds, p2p_pipeline_t** out) {
+    return guarded([&] {
+        P2P_CHECK(e && out, "NULL argument");
+        *out = nullptr;
+        std::unique_ptr<p2p_pipeline> h(new p2p_pipeline);
+        h->p.reset(new Pipeline(e->e.get(), max_dets, n_thresholds));
+        *out = h.release();
+    });
+}
+void p2p_pipeline_destroy(p2p_pipeline_t* p) { delete p; }
+
+int p2p_pipeline_run_device(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames_dev, int F, int H, int W,
+                            const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                            int iters, double confidence, p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p && m, "NULL argument");
+        p->p->run(*m->m, frames_dev, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
+                  confidence, reinterpret_cast<PoseRecord*>(out));
+    });
+}
+
+int p2p_pipeline_run(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames, int F, int H, int W,
+                     const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                     int iters, double confidence, p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p && m && frames, "NULL argument");
+        P2P_CHECK(F >= 1 && H >= 1 && W >= 1, "bad frame batch shape");
+        const uint8_t* fd = p->p->upload_frames(frames, F, H, W);
+        p->p->run(*m->m, fd, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
+                  confidence, reinterpret_cast<PoseRecord*>(out));
+    });
+}
+
+int p2p_pipeline_fetch_crop(p2p_pipeline_t* p, int det, const p2p_pose_t* rec, uint8_t* xyz, uint8_t* mask) {
+    return guarded([&] {
+        P2P_CHECK(p && rec, "NULL argument");
+        p->p->fetch_crop(det, *reinterpret_cast<const PoseRecord*>(rec), xyz, mask);
+    });
+}
+int p2p_pipeline_fetch_decode(p2p_pipeline_t* p, int stage, int index, float* out) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->fetch_decode(stage, index, out);
+    });
+}
+int p2p_pipeline_fetch_buffer(p2p_pipeline_t* p, int what, int index, float* out) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->fetch_buffer(what, index, out);
+    });
+}
+int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decode, const float* prob, int n) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->set_override(stage, decode, prob, n);
+    });
+}
+long long p2p_pipeline_launch_count(const p2p_pipeline_t* p) { return p ? p->p->launches + p->p->pnp.launches : 0; }
 
 int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,
                      float* ms_per_iter) {

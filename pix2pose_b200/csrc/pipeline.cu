@@ -1,0 +1,580 @@
+// Device pipeline of est_pose.  See pipeline.cuh; line references are into
+// pix2pose_model/recognition.py of the reference.
+#include "pipeline.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace p2p {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// resize helpers: skimage.transform.resize(order=1) semantics as pinned in oracle/resize_oracle.py
+struct Lerp { int lo, hi; double w; };
+
+__device__ __forceinline__ Lerp axis_map(int o, int n_in, int n_out) {
+    const double src = (o + 0.5) * (static_cast<double>(n_in) / n_out) - 0.5;
+    const double f = floor(src);
+    Lerp l;
+    l.lo = static_cast<int>(f);
+    l.hi = static_cast<int>(ceil(src));
+    l.w = src - f;
+    return l;
+}
+__device__ __forceinline__ int reflect_idx(int i, int dim) {
+    if (dim == 1) return 0;
+    const int cmax = dim - 1, period = 2 * cmax;
+    i = i < 0 ? -i : i;
+    i %= period;
+    return i > cmax ? period - i : i;
+}
+__device__ __forceinline__ double bilerp(double p00, double p01, double p10, double p11, double wr, double wc) {
+    const double top = (1 - wc) * p00 + wc * p01;
+    const double bot = (1 - wc) * p10 + wc * p11;
+    return (1 - wr) * top + wr * bot;
+}
+// clip=True of skimage warp: clip to the input range, keeping pixels that are exactly cval when cval is outside it
+__device__ __forceinline__ double clip_keep(double v, double mn, double mx, double cval) {
+    const bool keep = !(mn <= cval && cval <= mx);
+    if (keep && v == cval) return v;
+    return fmin(fmax(v, mn), mx);
+}
+// float32 L2 norm over 3 channels exactly as np.linalg.norm(x, axis=2) evaluates it for float32 input
+__device__ __forceinline__ float norm3_f32(float a, float b, float c) {
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+}
+
+// recognition.py:28-69 in double / int arithmetic (Python float == double, int() truncates)
+__device__ void get_boxes_dev(double box_size, const double* bbox, int v_max, int u_max, bool has_ct, int ct_v, int ct_u,
+                              double max_w, int* o) {
+    if (!has_ct) {
+        ct_v = static_cast<int>((bbox[0] + bbox[2]) / 2);
+        ct_u = static_cast<int>((bbox[1] + bbox[3]) / 2);
+    }
+    const double width = bbox[3] - bbox[1], height = bbox[2] - bbox[0];
+    const double w = fmin(max_w, fmax(width * box_size, height * box_size));
+    const int half = static_cast<int>(w / 2);
+    const int v1o = ct_v - half, v2o = ct_v + half, u1o = ct_u - half, u2o = ct_u + half;
+    int v1 = v1o, v2 = v2o, u1 = u1o, u2 = u2o, svn = 0, svx = 0, sun = 0, sux = 0;
+    if (v1o < 0) { svn = -v1o; v1 = 0; }
+    if (v2o > v_max) { svx = -(v2o - v_max); v2 = v_max; }
+    if (u1o < 0) { sun = -u1o; u1 = 0; }
+    if (u2o > u_max) { sux = -(u2o - u_max); u2 = u_max; }
+    o[0] = v1o; o[1] = v2o; o[2] = u1o; o[3] = u2o; o[4] = v1; o[5] = v2; o[6] = u1; o[7] = u2;
+    o[8] = svn; o[9] = svx + (v2o - v1o); o[10] = sun; o[11] = sux + (u2o - u1o);
+}
+
+// size guards of recognition.py:78 / :116-118 for a box
+__device__ __forceinline__ bool box_too_small(const int* b) {
+    return (b[1] - b[0]) < 5 || (b[3] - b[2]) < 5 || (b[5] - b[4]) < 5 || (b[7] - b[6]) < 5 || (b[9] - b[8]) <= 0 ||
+           (b[11] - b[10]) <= 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// P1 / P3: crop + normalise + zero-pad + bilinear resize to 128x128 ('reflect'); P3 also zeroes the
+// background given by the resized stage-1 mask (recognition.py:75-82, :103-121)
+template <bool STAGE2>
+__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                          const DetIn* __restrict__ dets, const DetState* __restrict__ state,
+                                                          const uint8_t* __restrict__ bits1, int n_th, float* __restrict__ x) {
+    int d, k = 0;
+    if (STAGE2) { d = blockIdx.x / n_th; k = blockIdx.x % n_th; } else { d = blockIdx.x; }
+    const DetIn& det = dets[d];
+    if (det.skip) return;
+    const int* b1 = det.box1;
+    const int* b = b1;
+    long long out_idx = d;
+    int tbit = 0, mask_all = 0;
+    if (STAGE2) {
+        const DetState& st = state[d];
+        if (k >= st.n_cand) return;
+        b = st.own_box[k];
+        tbit = st.cand_th[k];
+        mask_all = st.mask_all[k];
+        out_idx = st.cand_base + k;
+    }
+    const int p = blockIdx.y * 256 + threadIdx.x;
+    const int oy = p >> 7, ox = p & 127;
+    const int side_v = b[1] - b[0], side_u = b[3] - b[2];
+    const Lerp ly = axis_map(oy, side_v, 128), lx = axis_map(ox, side_u, 128);
+    const int rr[2] = {reflect_idx(ly.lo, side_v), reflect_idx(ly.hi, side_v)};
+    const int cc[2] = {reflect_idx(lx.lo, side_u), reflect_idx(lx.hi, side_u)};
+    const uint8_t* fr = frames + static_cast<long long>(det.frame) * H * W * 3;
+    const int s1v = b1[1] - b1[0], s1u = b1[3] - b1[2];
+    double pix[2][2][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int r = rr[a], q = cc[c];
+            bool inside = r >= b[8] && r < b[9] && q >= b[10] && q < b[11];
+            int v = 0, u = 0;
+            if (inside) {
+                v = b[4] + r - b[8];
+                u = b[6] + q - b[10];
+                if (STAGE2) {
+                    // bg_full (:105-106): everything outside the stage-1 crop, and inside it the pixels whose
+                    // up-sampled mask (:103, constant cval=0, > 0.9) is off
+                    bool fg = v >= b1[4] && v < b1[5] && u >= b1[6] && u < b1[7];
+                    if (fg) {
+                        const int mr = v - b1[4] + b1[8], mc = u - b1[6] + b1[10];
+                        const Lerp my = axis_map(mr, 128, s1v), mx = axis_map(mc, 128, s1u);
+                        const uint8_t* bm = bits1 + static_cast<long long>(d) * 16384;
+                        auto tap = [&](int y, int xx) -> double {
+                            if (y < 0 || y >= 128 || xx < 0 || xx >= 128) return 0.0;
+                            return (bm[y * 128 + xx] >> tbit) & 1 ? 1.0 : 0.0;
+                        };
+                        double mv = bilerp(tap(my.lo, mx.lo), tap(my.lo, mx.hi), tap(my.hi, mx.lo), tap(my.hi, mx.hi), my.w, mx.w);
+                        if (mask_all) mv = clip_keep(mv, 1.0, 1.0, 0.0);
+                        fg = mv > 0.9;
+                    }
+                    inside = fg;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                pix[a][c][ch] = inside ? (static_cast<double>(fr[(static_cast<long long>(v) * W + u) * 3 + ch]) - 128.0) / 128.0 : 0.0;
+        }
+    float* o = x + (out_idx * 16384 + p) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+        o[ch] = static_cast<float>(bilerp(pix[0][0][ch], pix[0][1][ch], pix[1][0][ch], pix[1][1][ch], ly.w, lx.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2: stage-1 masks, counts, bbox / centroid reductions, refined boxes (recognition.py:85-111)
+__global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restrict__ dets, DetState* __restrict__ state,
+                                                          const float* __restrict__ dec1, const float* __restrict__ prob1,
+                                                          uint8_t* __restrict__ bits1, const double* __restrict__ th_o, int n_th,
+                                                          int H, int W, double box_size) {
+    __shared__ int s_cnt[kMaxTh], s_n, s_minv, s_maxv, s_minu, s_maxu;
+    __shared__ long long s_sumv, s_sumu;
+    const int d = blockIdx.x;
+    const DetIn& det = dets[d];
+    DetState& st = state[d];
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < kMaxTh; ++t) s_cnt[t] = 0;
+        s_n = 0; s_minv = 1 << 30; s_maxv = -1; s_minu = 1 << 30; s_maxu = -1; s_sumv = 0; s_sumu = 0;
+    }
+    __syncthreads();
+    if (det.skip) {
+        if (threadIdx.x == 0) { st.n_init = 0; st.n_cand = 0; }
+        return;
+    }
+    float thf[kMaxTh];
+    for (int t = 0; t < n_th; ++t) thf[t] = static_cast<float>(th_o[t]);
+    int cnt[kMaxTh] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 0, minv = 1 << 30, maxv = -1, minu = 1 << 30, maxu = -1;
+    long long sumv = 0, sumu = 0;
+    const float* dc = dec1 + static_cast<long long>(d) * 16384 * 3;
+    const float* pb = prob1 + static_cast<long long>(d) * 16384;
+    for (int p = threadIdx.x; p < 16384; p += blockDim.x) {
+        const bool ng = norm3_f32(dc[p * 3], dc[p * 3 + 1], dc[p * 3 + 2]) > 0.3f;  // :89
+        uint8_t bits = ng ? 0x80 : 0;
+        if (ng) {
+            const int v = p >> 7, u = p & 127;
+            ++n; minv = min(minv, v); maxv = max(maxv, v); minu = min(minu, u); maxu = max(maxu, u);
+            sumv += v; sumu += u;
+            const float pr = pb[p];
+            for (int t = 0; t < n_th; ++t)
+                if (pr < thf[t]) { bits |= 1u << t; ++cnt[t]; }  // :94-95
+        }
+        bits1[static_cast<long long>(d) * 16384 + p] = bits;
+    }
+    for (int t = 0; t < n_th; ++t) atomicAdd(&s_cnt[t], cnt[t]);
+    atomicAdd(&s_n, n);
+    atomicMin(&s_minv, minv); atomicMax(&s_maxv, maxv); atomicMin(&s_minu, minu); atomicMax(&s_maxu, maxu);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sumv), static_cast<unsigned long long>(sumv));
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sumu), static_cast<unsigned long long>(sumu));
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    st.n_init = s_n;
+    const int* b1 = det.box1;
+    const double cx_o = (det.bbox[3] + det.bbox[1]) / 2.0, cy_o = (det.bbox[2] + det.bbox[0]) / 2.0;  // :72-73
+    const int w_stage_1 = b1[1] - b1[0];
+    int appended[kMaxTh][12], n_app = 0, nc = 0;
+    for (int t = 0; t < n_th; ++t) {
+        if (s_cnt[t] < 10) continue;  // :96
+        if (s_n == 0) continue;       // :99
+        const double sv = (b1[1] - b1[0]) / 128.0, su = (b1[3] - b1[2]) / 128.0;
+        const double bb[4] = {s_minv * sv, s_minu * su, s_maxv * sv, s_maxu * su};                        // :101-102
+        const int cx_m = static_cast<int>((static_cast<double>(s_sumu) / s_n - (127 / 2.0)) + cx_o);     // :108
+        const int cy_m = static_cast<int>((static_cast<double>(s_sumv) / s_n - (127 / 2.0)) + cy_o);     // :109
+        int box2[12];
+        get_boxes_dev(box_size, bb, H, W, true, cy_m, cx_m, static_cast<double>(w_stage_1), box2);        // :110
+        for (int i = 0; i < 12; ++i) appended[n_app][i] = box2[i];                                        // :111
+        ++n_app;
+        if (box_too_small(box2)) continue;                                                                // :116-119
+        st.cand_th[nc] = t;
+        st.mask_all[nc] = s_cnt[t] == 16384;
+        for (int i = 0; i < 12; ++i) st.own_box[nc][i] = box2[i];
+        ++nc;
+    }
+    for (int k = 0; k < nc; ++k)
+        for (int i = 0; i < 12; ++i) st.pair_box[k][i] = appended[k][i];  // quirk Q1: k-th output pairs with k-th appended box
+    st.n_cand = nc;
+}
+
+// compact candidate numbering over the batch + per-chunk live counts for the stage-2 forwards
+__global__ void cand_scan_kernel(DetState* __restrict__ state, CandStats* __restrict__ cands, int n_det, int* __restrict__ n_active,
+                                 int n_chunks, int chunk) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int base = 0;
+    for (int d = 0; d < n_det; ++d) {
+        state[d].cand_base = base;
+        for (int k = 0; k < state[d].n_cand; ++k) {
+            cands[base + k].det = d;
+            cands[base + k].k = k;
+        }
+        base += state[d].n_cand;
+    }
+    for (int j = 0; j < n_chunks; ++j) n_active[j] = max(0, min(chunk, base - j * chunk));
+    n_active[n_chunks] = base;  // total
+}
+
+// ------------------------------------------------------------------------------------------------
+// P4: stage-2 post-processing per candidate (recognition.py:132-154, :196-213)
+constexpr int kPostThreads = 512;
+
+__global__ void __launch_bounds__(kPostThreads) stage2_post_kernel(const DetIn* __restrict__ dets, const DetState* __restrict__ state,
+                                                                   CandStats* __restrict__ cands, const int* __restrict__ n_total,
+                                                                   const float* __restrict__ dec2, const float* __restrict__ prob2,
+                                                                   int n_th, double th_i, uint8_t* __restrict__ xyz_u8,
+                                                                   uint8_t* __restrict__ valid, float* __restrict__ obj,
+                                                                   float* __restrict__ img, PnpProblem* __restrict__ problems) {
+    const int c = blockIdx.x;
+    if (c >= *n_total) {
+        return;
+    }
+    __shared__ float s_pmin, s_pmax, s_imin, s_imax;
+    __shared__ int s_ng128, s_warp[kPostThreads / 32], s_base, s_nng;
+    __shared__ long long s_sv, s_su;
+    CandStats& cs = cands[c];
+    const int d = cs.det, k = cs.k;
+    const DetIn& det = dets[d];
+    const int* b = state[d].pair_box[k];
+    const float* dc = dec2 + static_cast<long long>(c) * 16384 * 3;
+    const float* pb = prob2 + static_cast<long long>(c) * 16384;
+    if (threadIdx.x == 0) {
+        s_pmin = 3.4e38f; s_pmax = -3.4e38f; s_imin = 3.4e38f; s_imax = -3.4e38f; s_ng128 = 0; s_base = 0; s_nng = 0; s_sv = 0; s_su = 0;
+    }
+    __syncthreads();
+    // ---- phase A: ranges needed by the clip of the three resizes
+    {
+        float pmin = 3.4e38f, pmax = -3.4e38f, imin = 3.4e38f, imax = -3.4e38f;
+        int ng = 0;
+        for (int p = threadIdx.x; p < 16384; p += blockDim.x) {
+            const float x = dc[p * 3], y = dc[p * 3 + 1], z = dc[p * 3 + 2];
+            const bool gray = norm3_f32(x, y, z) < 0.3f;  // :137
+            ng += gray ? 0 : 1;
+            const float pr = pb[p];
+            pmin = fminf(pmin, pr); pmax = fmaxf(pmax, pr);
+            const float v[3] = {x, y, z};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float ip = __fdiv_rn(__fadd_rn(gray ? 0.f : v[ch], 1.f), 2.f);  // :139-143
+                ip = fminf(fmaxf(ip, 0.f), 1.f);
+                imin = fminf(imin, ip); imax = fmaxf(imax, ip);
+            }
+        }
+        // float atomics via int reinterpretation are awkward for negatives: reduce through shuffles instead
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+            pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            imin = fminf(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+            imax = fmaxf(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+            ng += __shfl_xor_sync(0xffffffffu, ng, o);
+        }
+        __shared__ float s_r[4][kPostThreads / 32];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { s_r[0][warp] = pmin; s_r[1][warp] = pmax; s_r[2][warp] = imin; s_r[3][warp] = imax; atomicAdd(&s_ng128, ng); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < kPostThreads / 32; ++w) {
+                s_pmin = fminf(s_pmin, s_r[0][w]); s_pmax = fmaxf(s_pmax, s_r[1][w]);
+                s_imin = fminf(s_imin, s_r[2][w]); s_imax = fmaxf(s_imax, s_r[3][w]);
+            }
+        }
+        __syncthreads();
+    }
+    const double pmin = s_pmin, pmax = s_pmax, imin = s_imin, imax = s_imax;
+    const double gmin = s_ng128 == 16384 ? 1.0 : 0.0, gmax = s_ng128 > 0 ? 1.0 : 0.0;
+    // ---- phase B: resize back to the crop, quantise, masks, ordered compaction
+    const int side_v = b[1] - b[0], side_u = b[3] - b[2];
+    const int h = b[5] - b[4], w = b[7] - b[6];
+    const long long pool = det.pool_off + static_cast<long long>(k) * det.cap_px;
+    const int npx = (h > 0 && w > 0) ? h * w : 0;
+    int nng = 0;
+    long long sv = 0, su = 0;
+    for (int base = 0; base < npx; base += blockDim.x) {
+        const int q = base + threadIdx.x;
+        bool is_valid = false;
+        float o3[3] = {0, 0, 0};
+        int i = 0, j = 0;
+        if (q < npx) {
+            i = q / w; j = q - i * w;
+            const Lerp ly = axis_map(i + b[8], 128, side_v), lx = axis_map(j + b[10], 128, side_u);
+            const int ys[2] = {ly.lo, ly.hi}, xs[2] = {lx.lo, lx.hi};
+            double tp[2][2], tg[2][2], tx[2][2][3];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int y = ys[a], x = xs[e];
+                    if (y < 0 || y >= 128 || x < 0 || x >= 128) {
+                        tp[a][e] = 1.0; tg[a][e] = 0.0; tx[a][e][0] = tx[a][e][1] = tx[a][e][2] = 0.5;  // cval 1 / 0 / 0.5
+                    } else {
+                        const int p = y * 128 + x;
+                        const float vx = dc[p * 3], vy = dc[p * 3 + 1], vz = dc[p * 3 + 2];
+                        const bool gray = norm3_f32(vx, vy, vz) < 0.3f;
+                        tp[a][e] = pb[p];
+                        tg[a][e] = gray ? 0.0 : 1.0;
+                        const float v3[3] = {vx, vy, vz};
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float ip = __fdiv_rn(__fadd_rn(gray ? 0.f : v3[ch], 1.f), 2.f);
+                            tx[a][e][ch] = fminf(fmaxf(ip, 0.f), 1.f);
+                        }
+                    }
+                }
+            const double prob_ori = clip_keep(bilerp(tp[0][0], tp[0][1], tp[1][0], tp[1][1], ly.w, lx.w), pmin, pmax, 1.0);  // :134
+            const bool ng = clip_keep(bilerp(tg[0][0], tg[0][1], tg[1][0], tg[1][1], ly.w, lx.w), gmin, gmax, 0.0) > 0.9;   // :146
+            uint8_t u8[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const double v = clip_keep(bilerp(tx[0][0][ch], tx[0][1][ch], tx[1][0][ch], tx[1][1][ch], ly.w, lx.w), imin, imax, 0.5) * 255;  // :144
+                u8[ch] = static_cast<uint8_t>(static_cast<int>(v));  // :154 float -> uint8 truncation
+                xyz_u8[(pool + q) * 3 + ch] = u8[ch];
+                o3[ch] = static_cast<float>((static_cast<double>(u8[ch]) / 255 * 2 - 1) * det.scale[ch] + det.ct[ch]);  // :198-202
+            }
+            if (ng) { ++nng; sv += i + b[4]; su += j + b[6]; }
+            is_valid = ng && prob_ori < th_i;  // :203-204
+            valid[pool + q] = is_valid ? 1 : 0;
+        }
+        // ordered (row-major) compaction of the valid pixels of this chunk
+        const unsigned ball = __ballot_sync(0xffffffffu, is_valid);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) s_warp[warp] = __popc(ball);
+        __syncthreads();
+        int before = s_base;
+        for (int wv = 0; wv < warp; ++wv) before += s_warp[wv];
+        if (is_valid) {
+            const long long dst = pool + before + __popc(ball & ((1u << lane) - 1));
+            obj[dst * 3] = o3[0]; obj[dst * 3 + 1] = o3[1]; obj[dst * 3 + 2] = o3[2];
+            img[dst * 2] = static_cast<float>(j + b[6]);      // u + u1  (:209-211)
+            img[dst * 2 + 1] = static_cast<float>(i + b[4]);  // v + v1
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int wv = 0; wv < kPostThreads / 32; ++wv) tot += s_warp[wv];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    atomicAdd(&s_nng, nng);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_sv), static_cast<unsigned long long>(sv));
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_su), static_cast<unsigned long long>(su));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cs.n_non_gray = s_nng;
+        cs.skipped = s_nng < 10 ? 1 : 0;  // :149-150
+        cs.n_pts = cs.skipped ? 0 : s_base;
+        cs.sum_v = static_cast<double>(s_sv);
+        cs.sum_u = static_cast<double>(s_su);
+        PnpProblem pr;
+        pr.offset = pool; pr.n = cs.n_pts; pr.pad = 0;
+        pr.fu = det.fu; pr.fv = det.fv; pr.uc = det.uc; pr.vc = det.vc;
+        problems[c] = pr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P5: candidate selection (recognition.py:158-178, :189-193)
+__global__ void select_kernel(const DetIn* __restrict__ dets, const DetState* __restrict__ state, const CandStats* __restrict__ cands,
+                              const PnpResult* __restrict__ pnp, PoseRecord* __restrict__ recs, int n_det) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_det) return;
+    const DetIn& det = dets[d];
+    const DetState& st = state[d];
+    PoseRecord r;
+    for (int i = 0; i < 9; ++i) r.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    r.t[0] = r.t[1] = r.t[2] = 0;
+    r.frac_inlier = -1; r.status = det.skip ? -2 : 0; r.n_inliers = -1; r.best_cand = -1; r.n_cand = st.n_cand;
+    r.n_init = st.n_init; r.mask_all_true = 0; r.cand_base = st.cand_base; r.pad = 0;
+    for (int i = 0; i < 4; ++i) r.bbox_t[i] = det.box1[4 + i];
+    for (int i = 0; i < 12; ++i) r.best_box[i] = det.box1[i];
+    int max_inlier = -1;
+    double min_dist = 9999999;
+    for (int k = 0; k < st.n_cand; ++k) {
+        const int c = st.cand_base + k;
+        const int* b = st.pair_box[k];
+        for (int i = 0; i < 4; ++i) r.bbox_t[i] = b[4 + i];  // quirk Q2: loop variables survive the loop
+        const CandStats& cs = cands[c];
+        if (cs.skipped) continue;
+        const PnpResult& pr = pnp[c];
+        const bool ok = pr.status == 1;
+        const int n_inl = ok ? pr.n_inliers : -1;
+        const double tz = ok ? pr.tvec[2] : 0.0;
+        double dist;
+        if (tz == 0) {
+            dist = 99999;
+        } else {
+            const double ctv = cs.sum_v / cs.n_non_gray, ctu = cs.sum_u / cs.n_non_gray;
+            const double pu = det.fu * pr.tvec[0] / tz + det.uc, pv = det.fv * pr.tvec[1] / tz + det.vc;
+            dist = ((pv - ctv) * (pv - ctv) + (pu - ctu) * (pu - ctu)) / (n_inl + 1e-6);
+        }
+        if (dist < min_dist) {
+            min_dist = dist;
+            max_inlier = n_inl;
+            r.best_cand = k;
+            for (int i = 0; i < 9; ++i) r.R[i] = ok ? pr.R[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+            for (int i = 0; i < 3; ++i) r.t[i] = ok ? pr.tvec[i] : 0.0;
+            for (int i = 0; i < 12; ++i) r.best_box[i] = b[i];
+            r.mask_all_true = pr.status == 0 ? 1 : 0;
+        }
+    }
+    r.n_inliers = max_inlier;
+    if (max_inlier != -1) {
+        r.status = 1;
+        r.frac_inlier = static_cast<double>(max_inlier) / st.n_init;
+    }
+    recs[d] = r;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+Pipeline::Pipeline(Engine* eng, int max_dets_, int n_th_) : engine(eng), max_dets(max_dets_), n_th(n_th_) {
+    P2P_CHECK(n_th >= 1 && n_th <= 7, "number of outlier thresholds must be in [1,7], got %d", n_th);
+    P2P_CHECK(max_dets >= 1, "max_dets must be positive");
+    const size_t D = max_dets, C = static_cast<size_t>(max_dets) * n_th;
+    dets_.alloc(D); state_.alloc(D); cands_.alloc(C); recs_.alloc(D);
+    x1_.alloc(D * 16384 * 3); dec1_.alloc(D * 16384 * 3); prob1_.alloc(D * 16384);
+    x2_.alloc(C * 16384 * 3); dec2_.alloc(C * 16384 * 3); prob2_.alloc(C * 16384);
+    bits1_.alloc(D * 16384);
+    n_active_.alloc(C / std::max(1, eng->cap) + 3);
+    th_.alloc(kMaxTh);
+    problems_.alloc(C); pnp_res_.alloc(C);
+}
+Pipeline::~Pipeline() {}
+
+void Pipeline::ensure_pool(long long px) {
+    if (px <= pool_px_) return;
+    pool_px_ = px + px / 4;
+    xyz_u8_.alloc(pool_px_ * 3); valid_.alloc(pool_px_); pnp_mask_.alloc(pool_px_);
+    obj_.alloc(pool_px_ * 3); img_.alloc(pool_px_ * 2);
+}
+
+void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, int W, const DetIn* dets, int n,
+                   const double* th_o, double th_i, float reproj_err, int iters, double confidence, PoseRecord* out) {
+    P2P_CHECK(n >= 0 && n <= max_dets, "run: %d detections, pipeline built for %d", n, max_dets);
+    if (n == 0) return;
+    P2P_CHECK(frames_dev && dets && th_o && out, "NULL argument");
+    cudaStream_t s = engine->stream;
+    host_dets_.assign(dets, dets + n);
+    long long px = 0;
+    for (int d = 0; d < n; ++d) {
+        DetIn& di = host_dets_[d];
+        P2P_CHECK(di.frame >= 0 && di.frame < F, "detection %d: frame %d outside [0,%d)", d, di.frame, F);
+        const long long side = std::max(0, di.box1[1] - di.box1[0]);
+        di.cap_px = static_cast<int>(std::min<long long>(side * side, 1 << 30));
+        di.pool_off = px;
+        px += static_cast<long long>(di.cap_px) * n_th;
+    }
+    ensure_pool(px + 1);
+    dets_.upload(host_dets_.data(), n, s);
+    double th[kMaxTh] = {0};
+    for (int t = 0; t < n_th; ++t) th[t] = th_o[t];
+    th_.upload(th, kMaxTh, s);
+    const int cap = engine->cap;
+
+    // stage 1
+    crop_resize_kernel<false><<<dim3(n, 64), 256, 0, s>>>(frames_dev, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
+    P2P_CUDA(cudaGetLastError());
+    for (int b = 0; b < n; b += cap) {
+        const int nb = std::min(cap, n - b);
+        engine->forward(model, x1_.p + static_cast<size_t>(b) * 16384 * 3, nb, dec1_.p + static_cast<size_t>(b) * 16384 * 3,
+                        prob1_.p + static_cast<size_t>(b) * 16384, nullptr, s);
+    }
+    if (!ov_dec_[0].empty()) {
+        P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaStreamSynchronize(s));
+        ov_dec_[0].clear(); ov_prob_[0].clear();
+    }
+    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, th_.p, n_th, H, W, 1.5);
+    P2P_CUDA(cudaGetLastError());
+    const int C = n * n_th;
+    const int n_chunks = (C + cap - 1) / cap;
+    cand_scan_kernel<<<1, 32, 0, s>>>(state_.p, cands_.p, n, n_active_.p, n_chunks, cap);
+    P2P_CUDA(cudaGetLastError());
+    // stage 2
+    crop_resize_kernel<true><<<dim3(C, 64), 256, 0, s>>>(frames_dev, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
+    P2P_CUDA(cudaGetLastError());
+    for (int j = 0; j < n_chunks; ++j) {
+        const int nb = std::min(cap, C - j * cap);
+        engine->forward(model, x2_.p + static_cast<size_t>(j) * cap * 16384 * 3, nb, dec2_.p + static_cast<size_t>(j) * cap * 16384 * 3,
+                        prob2_.p + static_cast<size_t>(j) * cap * 16384, n_active_.p + j, s);
+    }
+    if (!ov_dec_[1].empty()) {
+        P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaStreamSynchronize(s));
+        ov_dec_[1].clear(); ov_prob_[1].clear();
+    }
+    P2P_CUDA(cudaMemsetAsync(problems_.p, 0, sizeof(PnpProblem) * C, s));  // slots past the live count: n = 0 -> skipped
+    stage2_post_kernel<<<C, kPostThreads, 0, s>>>(dets_.p, state_.p, cands_.p, n_active_.p + n_chunks, dec2_.p, prob2_.p, n_th, th_i,
+                                                  xyz_u8_.p, valid_.p, obj_.p, img_.p, problems_.p);
+    P2P_CUDA(cudaGetLastError());
+    launches += 5;
+    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s);
+    select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
+    P2P_CUDA(cudaGetLastError());
+    launches += 1;
+    P2P_CUDA(cudaMemcpyAsync(out, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
+    P2P_CUDA(cudaStreamSynchronize(s));
+}
+
+void Pipeline::fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out) {
+    P2P_CHECK(d >= 0 && d < static_cast<int>(host_dets_.size()), "fetch_crop: bad detection index");
+    P2P_CHECK(rec.best_cand >= 0, "fetch_crop: detection has no winning candidate");
+    const DetIn& di = host_dets_[d];
+    const long long pool = di.pool_off + static_cast<long long>(rec.best_cand) * di.cap_px;
+    const int h = rec.best_box[5] - rec.best_box[4], w = rec.best_box[7] - rec.best_box[6];
+    const size_t npx = static_cast<size_t>(std::max(h, 0)) * std::max(w, 0);
+    if (xyz_out) P2P_CUDA(cudaMemcpy(xyz_out, xyz_u8_.p + pool * 3, npx * 3, cudaMemcpyDeviceToHost));
+    if (mask_out) P2P_CUDA(cudaMemcpy(mask_out, valid_.p + pool, npx, cudaMemcpyDeviceToHost));
+}
+
+void Pipeline::fetch_decode(int stage, int index, float* out) {
+    P2P_CHECK(stage == 1 || stage == 2, "stage must be 1 or 2");
+    fetch_buffer(stage, index, out);
+}
+
+void Pipeline::fetch_buffer(int what, int index, float* out) {
+    P2P_CHECK(what >= 1 && what <= 6 && out, "fetch_buffer: bad selector %d", what);
+    const bool s2 = what == 2 || what == 4 || what == 6;
+    const size_t lim = s2 ? static_cast<size_t>(max_dets) * n_th : static_cast<size_t>(max_dets);
+    P2P_CHECK(index >= 0 && static_cast<size_t>(index) < lim, "fetch_buffer: bad index %d", index);
+    const float* base[7] = {nullptr, dec1_.p, dec2_.p, x1_.p, x2_.p, prob1_.p, prob2_.p};
+    const size_t cnt = what >= 5 ? 16384 : 16384 * 3;
+    P2P_CUDA(cudaMemcpy(out, base[what] + static_cast<size_t>(index) * cnt, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+void Pipeline::set_override(int stage, const float* dec, const float* prob, int n) {
+    P2P_CHECK((stage == 1 || stage == 2) && dec && prob && n >= 0, "set_override: bad argument");
+    ov_dec_[stage - 1].assign(dec, dec + static_cast<size_t>(n) * 16384 * 3);
+    ov_prob_[stage - 1].assign(prob, prob + static_cast<size_t>(n) * 16384);
+}
+
+const uint8_t* Pipeline::upload_frames(const uint8_t* frames_host, int F, int H, int W) {
+    const size_t bytes = static_cast<size_t>(F) * H * W * 3;
+    if (frames_.n < bytes) frames_.alloc(bytes);
+    P2P_CUDA(cudaMemcpyAsync(frames_.p, frames_host, bytes, cudaMemcpyHostToDevice, engine->stream));
+    return frames_.p;
+}
+
+}  // namespace p2p

@@ -1,0 +1,112 @@
+// Batched device pipeline of pix2pose.est_pose (pix2pose_model/recognition.py:70-193): everything
+// between the two network forwards and after the second one runs on the GPU with no host
+// round-trip: crop / normalise / bilinear resize (:75-82, :113-121), stage-1 masks, counts, bbox and
+// centroid reductions and the refined boxes (:85-111), stage-2 resize-back, uint8 quantisation, mask
+// and the row-major correspondence compaction (:132-154, :196-213), then PnP-RANSAC
+// (pnp_ransac.cuh) and the candidate selection (:158-178, :189-193).
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "pnp_ransac.cuh"
+
+namespace p2p {
+
+constexpr int kMaxTh = 8;  // outlier thresholds per detection (reference configs use 1, 3 or 4)
+
+// One detection = one est_pose(rgb, bbox) call.  Filled by the host.
+struct DetIn {
+    int frame;        // index into the frame batch
+    int skip;         // 1: stage-1 size guard tripped (recognition.py:78-79) -> status -2
+    int bbox[4];      // roi [v0,u0,v1,u1] as passed to est_pose
+    int box1[12];     // get_boxes(bbox, H, W) (recognition.py:71)
+    double fu, fv, uc, vc;      // self.camK at call time
+    double scale[3], ct[3];     // obj_param (recognition.py:17-18)
+    long long pool_off;         // first pixel slot of this detection's candidate pools
+    int cap_px;                 // pixels reserved per candidate (side1^2)
+    int pad;
+};
+
+// Stage-1 statistics and the stage-2 candidates of one detection (device-written).
+struct DetState {
+    int n_init;                 // np.sum(non_gray), recognition.py:90
+    int n_cand;                 // len(input_refined)
+    int cand_th[kMaxTh];        // threshold index whose crop feeds candidate k
+    int own_box[kMaxTh][12];    // refined box the crop of candidate k was cut with
+    int pair_box[kMaxTh][12];   // box_refined[k]: the box stage 2 pairs with network output k (quirk Q1)
+    int mask_all[kMaxTh];       // 1 when every one of the 128x128 pixels passed (resize clip corner case)
+    int cand_base;              // first compact candidate index of this detection
+    int pad;
+};
+
+struct CandStats {              // per compact candidate, written by stage-2 post
+    int det, k;
+    int n_non_gray;             // np.sum(non_gray) after resize-back (:148)
+    int skipped;                // 1: n_non_gray < 10 (:149-150)
+    int n_pts;                  // correspondences (valid_mask pixels)
+    int pad;
+    double sum_v, sum_u;        // frame coordinates of the non_gray pixels (centroid, :159-162)
+};
+
+struct PoseRecord {             // est_pose result of one detection
+    double R[9], t[3];
+    double frac_inlier;         // max_inlier / n_init_mask, or -1
+    int status;                 // 1 ok; 0 no valid pose (reference returns -1 sentinels); -2 size guard
+    int n_inliers;
+    int best_cand;              // k of the winning candidate, -1 if none
+    int n_cand;
+    int bbox_t[4];              // [v1,v2,u1,u2] the reference returns (quirk Q2)
+    int best_box[12];           // paired box of the winner (where img_pred_f / valid_mask live)
+    int n_init;
+    int mask_all_true;          // 1: PnP returned inliers=None -> valid_mask = -1 -> all-true mask (:219, :177)
+    int cand_base;              // compact index of this detection's first candidate (for fetch_decode)
+    int pad;
+};
+
+class Pipeline {
+  public:
+    Pipeline(Engine* engine, int max_dets, int n_th);
+    ~Pipeline();
+    // frames_dev: (F,H,W,3) uint8 on the device; dets: host array of n (<= max_dets).
+    // Results are copied to `out` (host).  th_o has n_th entries.
+    void run(const Model& model, const uint8_t* frames_dev, int F, int H, int W, const DetIn* dets, int n,
+             const double* th_o, double th_i, float reproj_err, int iters, double confidence, PoseRecord* out);
+    // After run(): copy the winner's uint8 XYZ crop (h,w,3) and valid mask (h,w) of detection d
+    // (h = v2-v1, w = u2-u1 of best_box) into host buffers sized for cap_px pixels.
+    void fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out);
+    // Raw network output (128,128,3) of stage 1 (index = detection) or stage 2 (index = compact candidate).
+    void fetch_decode(int stage, int index, float* out);
+    // Debug / parity: raw float buffers. what: 1 dec1, 2 dec2, 3 x1, 4 x2 ((128,128,3) each), 5 prob1, 6 prob2 ((128,128)).
+    void fetch_buffer(int what, int index, float* out);
+    // Test hook: replace the network outputs of `stage` (1|2) in the NEXT run by these host arrays
+    // (n crops of decode (128,128,3) and prob (128,128)); used by planted-pose parity tests only.
+    void set_override(int stage, const float* dec, const float* prob, int n);
+    // Host frames (F,H,W,3) uint8 -> device copy owned by the pipeline.
+    const uint8_t* upload_frames(const uint8_t* frames_host, int F, int H, int W);
+    long long launches = 0;
+    Engine* engine;
+    PnpSolver pnp;
+    int max_dets, n_th;
+
+  private:
+    void ensure_pool(long long px);
+    DevBuf<DetIn> dets_;
+    DevBuf<DetState> state_;
+    DevBuf<CandStats> cands_;
+    DevBuf<PoseRecord> recs_;
+    DevBuf<float> x1_, dec1_, prob1_, x2_, dec2_, prob2_;
+    DevBuf<uint8_t> bits1_;       // (D,128,128): bit t = non_gray & prob<th_t ; bit 7 = non_gray
+    DevBuf<int> n_active_;        // per stage-2 chunk
+    DevBuf<double> th_;
+    DevBuf<uint8_t> xyz_u8_, valid_, pnp_mask_;
+    DevBuf<float> obj_, img_;
+    DevBuf<PnpProblem> problems_;
+    DevBuf<PnpResult> pnp_res_;
+    DevBuf<uint8_t> frames_;
+    std::vector<float> ov_dec_[2], ov_prob_[2];
+    long long pool_px_ = 0;
+    std::vector<DetIn> host_dets_;
+};
+
+}  // namespace p2p

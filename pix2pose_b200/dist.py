@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), detections sharded by index, no data-path
+collective -- each detection is independent (tools/5_evaluation_bop_basic.py:289-323 has no cross-ROI
+state) -- and ONE gather of fixed-size pose records per batch (16 float64 per detection:
+R9, t3, n_inliers, frac_inlier, status, global index).  ``torch.distributed`` is plumbing only
+(NCCL on GPUs, gloo in the CPU tests)."""
+import os
+
+import numpy as np
+
+RECORD = 16
+
+
+def env_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard_indices(n, rank, world):
+    """Indices of the detections rank `rank` owns: i % world == rank (round-robin keeps per-object
+    sub-batches balanced when the stream interleaves objects)."""
+    return np.arange(rank, n, world, dtype=np.int64)
+
+
+def init(backend=None):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif world == 1 and torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, local_rank, world
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def gather_records(local_records, global_index, n_total, device=None):
+    """All ranks contribute (n_local, 16) records whose last column is overwritten with `global_index`;
+    every rank gets the (n_total, 16) array ordered by global detection index.  One all_gather of a
+    padded fixed-size tensor (<= 128 B per detection)."""
+    import torch
+    import torch.distributed as dist
+    rec = np.array(local_records, np.float64).reshape(-1, RECORD)
+    rec[:, RECORD - 1] = np.asarray(global_index, np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        out = np.zeros((n_total, RECORD))
+        out[rec[:, RECORD - 1].astype(np.int64)] = rec
+        return out
+    world = dist.get_world_size()
+    cap = (n_total + world - 1) // world
+    pad = np.full((cap, RECORD), -1.0)
+    pad[: rec.shape[0]] = rec
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(pad).to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    allr = torch.cat(parts).cpu().numpy()
+    allr = allr[allr[:, RECORD - 1] >= 0]
+    out = np.zeros((n_total, RECORD))
+    out[allr[:, RECORD - 1].astype(np.int64)] = allr
+    return out
+
+
+def max_over_ranks(value, device=None):
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

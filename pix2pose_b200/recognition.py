@@ -1,0 +1,262 @@
+"""Drop-in for ``pix2pose_model/recognition.py`` of kirumang/Pix2Pose on B200.
+
+``pix2pose(weight_fn, camK, res_x, res_y, obj_param, ...)`` keeps the reference's constructor,
+attributes (``camK`` is re-assigned by callers before every call,
+tools/5_evaluation_bop_basic.py:302), ``get_boxes``, ``est_pose`` and ``pnp_ransac`` signatures and
+return conventions (sentinel ``-1`` returns, never exceptions: recognition.py:79,127,191,215,219).
+All arithmetic of the hot path runs in CUDA behind include/pix2pose_b200.h:
+
+* ``generator_train.predict``  -> tcgen05 implicit-GEMM generator (csrc/conv_tc.cuh)
+* crop / resize / masks / uint8 XYZ / correspondences -> csrc/pipeline.cu
+* ``cv2.solvePnPRansac`` + ``cv2.Rodrigues`` -> csrc/pnp_ransac.cu
+
+``est_pose_batch`` is the throughput entry point (many detections, one device pipeline run);
+``est_pose`` is a batch of one.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, ae_model
+from .pnp import solve_pnp_ransac
+
+
+class _Det(ctypes.Structure):
+    _fields_ = [("frame", ctypes.c_int), ("skip", ctypes.c_int), ("bbox", ctypes.c_int * 4), ("box1", ctypes.c_int * 12),
+                ("fu", ctypes.c_double), ("fv", ctypes.c_double), ("uc", ctypes.c_double), ("vc", ctypes.c_double),
+                ("scale", ctypes.c_double * 3), ("ct", ctypes.c_double * 3),
+                ("pool_off", ctypes.c_longlong), ("cap_px", ctypes.c_int), ("pad", ctypes.c_int)]
+
+
+class _Pose(ctypes.Structure):
+    _fields_ = [("R", ctypes.c_double * 9), ("t", ctypes.c_double * 3), ("frac_inlier", ctypes.c_double),
+                ("status", ctypes.c_int), ("n_inliers", ctypes.c_int), ("best_cand", ctypes.c_int), ("n_cand", ctypes.c_int),
+                ("bbox_t", ctypes.c_int * 4), ("best_box", ctypes.c_int * 12), ("n_init", ctypes.c_int),
+                ("mask_all_true", ctypes.c_int), ("cand_base", ctypes.c_int), ("pad", ctypes.c_int)]
+
+
+def _get_boxes(box_size, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
+    """recognition.py:28-69, verbatim arithmetic (Python floats, ``int()`` truncation)."""
+    if ct[0] == -1:
+        bbox_ct_v = int((bbox[0] + bbox[2]) / 2)
+        bbox_ct_u = int((bbox[1] + bbox[3]) / 2)
+    else:
+        bbox_ct_v, bbox_ct_u = ct[0], ct[1]
+    width, height = bbox[3] - bbox[1], bbox[2] - bbox[0]
+    w = min(max_w, max(width * box_size, height * box_size))
+    half = int(w / 2)
+    lo_v, hi_v, lo_u, hi_u = bbox_ct_v - half, bbox_ct_v + half, bbox_ct_u - half, bbox_ct_u + half
+    cv1, cv2_, cu1, cu2 = lo_v, hi_v, lo_u, hi_u
+    pad_top = pad_left = cut_bottom = cut_right = 0
+    if lo_v < 0:
+        pad_top, cv1 = abs(lo_v), 0
+    if hi_v > v_max:
+        cut_bottom, cv2_ = -abs(hi_v - v_max), v_max
+    if lo_u < 0:
+        pad_left, cu1 = abs(lo_u), 0
+    if hi_u > u_max:
+        cut_right, cu2 = -abs(hi_u - u_max), u_max
+    return (lo_v, hi_v, lo_u, hi_u, cv1, cv2_, cu1, cu2, pad_top, cut_bottom + (hi_v - lo_v), pad_left,
+            cut_right + (hi_u - lo_u))
+
+
+class PoseBatchResult:
+    """Result of ``est_pose_batch``: struct-of-arrays view plus lazy crop access."""
+
+    def __init__(self, owner, poses, n):
+        self._owner, self._poses, self.n = owner, poses, n
+        self.status = np.array([poses[i].status for i in range(n)], np.int32)
+        self.R = np.array([list(poses[i].R) for i in range(n)], np.float64).reshape(n, 3, 3)
+        self.t = np.array([list(poses[i].t) for i in range(n)], np.float64).reshape(n, 3)
+        self.n_inliers = np.array([poses[i].n_inliers for i in range(n)], np.int32)
+        self.frac_inlier = np.array([poses[i].frac_inlier for i in range(n)], np.float64)
+        self.bbox_t = np.array([list(poses[i].bbox_t) for i in range(n)], np.int64).reshape(n, 4)
+        self.n_cand = np.array([poses[i].n_cand for i in range(n)], np.int32)
+
+    def records(self):
+        """(n, 16) float64 pose records for the multi-GPU gather: R9, t3, n_inliers, frac, status, index."""
+        rec = np.zeros((self.n, 16))
+        rec[:, :9] = self.R.reshape(self.n, 9)
+        rec[:, 9:12] = self.t
+        rec[:, 12], rec[:, 13], rec[:, 14] = self.n_inliers, self.frac_inlier, self.status
+        rec[:, 15] = np.arange(self.n)
+        return rec
+
+    def crop(self, d):
+        """(img_pred uint8 (h,w,3), valid_mask bool (h,w), box) of detection d's winning candidate."""
+        return self._owner._fetch_crop(d, self._poses[d])
+
+
+class pix2pose():
+    def __init__(self, weight_fn, camK, res_x, res_y, obj_param, th_ransac=3.0, th_outlier=[0.1, 0.2, 0.3], th_inlier=0.1,
+                 box_size=1.5, dist_coeff=None, backbone="paper", precision="fp16x3", capacity=64, max_dets=64, **kwargs):
+        # recognition.py:11-26
+        self.camK = camK
+        self.res_x = res_x
+        self.res_y = res_y
+        self.th_ransac = th_ransac      # stored, never used (reprojectionError is hard-coded to 5, recognition.py:217)
+        self.th_o = th_outlier
+        self.th_i = th_inlier
+        self.obj_scale = obj_param[:3]  # x,y,z
+        self.obj_ct = obj_param[3:]     # x,y,z
+        self.box_size = box_size
+        self.dist_coeff = dist_coeff    # stored, never used (distCoeffs=None, recognition.py:216)
+        if box_size != 1.5:
+            # the device-side refined-box arithmetic (csrc/pipeline.cu stage1_post_kernel) fixes the default
+            raise ValueError("box_size other than the reference default 1.5 is not supported")
+        if backbone == 'paper':
+            self.generator_train = ae_model.aemodel_unet_prob(p=1.0, precision=precision, capacity=capacity)
+        elif backbone == 'resnet50':
+            self.generator_train = ae_model.aemodel_unet_resnet50(p=1.0, precision=precision, capacity=capacity)
+        else:
+            raise ValueError("backbone must be 'paper' or 'resnet50'")
+        self.generator_train.load_weights(weight_fn)
+        self._pipe = None
+        self._pipe_key = None
+        self._max_dets = int(max_dets)
+        self._last = None
+
+    # ------------------------------------------------------------------------------------------------
+    def get_boxes(self, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
+        return _get_boxes(self.box_size, bbox, v_max, u_max, ct, max_w)
+
+    def _pipeline(self, n):
+        key = (len(self.th_o), max(self._max_dets, n))
+        if self._pipe is None or self._pipe_key[0] != key[0] or self._pipe_key[1] < n:
+            self._release_pipe()
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().p2p_pipeline_create(self.generator_train.engine.handle, key[1], key[0], ctypes.byref(h)))
+            self._pipe, self._pipe_key = h, key
+        return self._pipe
+
+    def _release_pipe(self):
+        if getattr(self, "_pipe", None) is not None:
+            _lib.lib().p2p_pipeline_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self._release_pipe()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        n = self.generator_train.engine.launch_count
+        if self._pipe is not None:
+            n += int(_lib.lib().p2p_pipeline_launch_count(self._pipe))
+        return n
+
+    def _make_dets(self, shape_hw, bboxes, frame_ids, camKs):
+        H, W = shape_hw
+        n = len(bboxes)
+        dets = (_Det * max(n, 1))()
+        for i in range(n):
+            bb = [int(v) for v in bboxes[i]]
+            box1 = self.get_boxes(bb, H, W)
+            d = dets[i]
+            d.frame = int(frame_ids[i])
+            d.bbox[:] = bb
+            d.box1[:] = [int(v) for v in box1]
+            side_v, side_u = box1[1] - box1[0], box1[3] - box1[2]
+            ph, pw = box1[5] - box1[4], box1[7] - box1[6]
+            d.skip = int(side_v < 5 or side_u < 5 or ph < 5 or pw < 5)   # recognition.py:78
+            K = np.asarray(camKs[i] if camKs is not None else self.camK, np.float64).reshape(3, 3)
+            d.fu, d.fv, d.uc, d.vc = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+            d.scale[:] = [float(v) for v in self.obj_scale]
+            d.ct[:] = [float(v) for v in self.obj_ct]
+        return dets
+
+    def est_pose_batch(self, frames, bboxes, frame_ids=None, camKs=None):
+        """Poses for many detections of this object in one device pipeline run.
+
+        frames: (F,H,W,3) uint8 (or a single (H,W,3) image); bboxes: (n,4) rois [v0,u0,v1,u1];
+        frame_ids: (n,) index of each roi's frame (default 0); camKs: optional per-detection intrinsics.
+        Returns a ``PoseBatchResult``; ``status``: 1 pose found, 0 the reference would return its -1
+        sentinels, -2 the crop was smaller than 5 px (recognition.py:78)."""
+        frames = np.asarray(frames)
+        if frames.ndim == 3:
+            frames = frames[None]
+        if frames.dtype != np.uint8:
+            # the ICP driver passes float32 images holding 0..255 (5_evaluation_bop_icp3d.py:369)
+            frames = frames.astype(np.uint8)
+        frames = np.ascontiguousarray(frames)
+        F, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
+        n = len(bboxes)
+        if frame_ids is None:
+            frame_ids = np.zeros(n, np.int64)
+        dets = self._make_dets((H, W), bboxes, frame_ids, camKs)
+        poses = (_Pose * max(n, 1))()
+        th = np.ascontiguousarray(np.asarray(self.th_o, np.float64))
+        pipe = self._pipeline(n)
+        _lib.check(_lib.lib().p2p_pipeline_run(
+            pipe, self.generator_train._model, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), F, H, W, dets, n,
+            th.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(self.th_i), 5.0, 100, 0.99, poses))
+        self._last = (dets, poses, n, (H, W))
+        return PoseBatchResult(self, poses, n)
+
+    def _fetch_crop(self, d, pose):
+        bx = list(pose.best_box)
+        h, w = max(bx[5] - bx[4], 0), max(bx[7] - bx[6], 0)
+        xyz = np.zeros((h, w, 3), np.uint8)
+        mask = np.zeros((h, w), np.uint8)
+        if h * w > 0:
+            _lib.check(_lib.lib().p2p_pipeline_fetch_crop(self._pipe, d, ctypes.byref(pose),
+                                                          xyz.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                                          mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+        if pose.mask_all_true:
+            mask[:] = 1
+        return xyz, mask.astype(bool), bx
+
+    def debug_fetch(self, what, index):
+        """Parity hook: float buffers of the last run (1 dec1, 2 dec2, 3 x1, 4 x2, 5 prob1, 6 prob2)."""
+        out = np.zeros((128, 128, 3) if what <= 4 else (128, 128), np.float32)
+        _lib.check(_lib.lib().p2p_pipeline_fetch_buffer(self._pipe, what, index, _lib.fptr(out)))
+        return out
+
+    def debug_override(self, stage, decode, prob, n_dets=1):
+        """Parity hook: the next run uses these arrays instead of the network outputs of `stage`."""
+        decode, prob = _lib.as_f32(decode), _lib.as_f32(prob)
+        self._pipeline(n_dets)
+        _lib.check(_lib.lib().p2p_pipeline_debug_override(self._pipe, stage, _lib.fptr(decode), _lib.fptr(prob), decode.shape[0]))
+
+    def _fetch_pred(self, stage, index, zero_gray):
+        dec = np.zeros((128, 128, 3), np.float32)
+        _lib.check(_lib.lib().p2p_pipeline_fetch_decode(self._pipe, stage, index, _lib.fptr(dec)))
+        if zero_gray:
+            dec[np.linalg.norm(dec, axis=2) < 0.3] = 0           # recognition.py:137-139
+        return np.clip((dec + 1) / 2, 0, 1)                       # :85-87 / :141-143
+
+    def est_pose(self, rgb, bbox, gt_trans=np.eye((4)), z_iter=False):
+        """recognition.py:70-193 -> (img_pred, mask_pred, rot_pred, tra_pred, frac_inlier, bbox_t)."""
+        res = self.est_pose_batch(rgb, [bbox])
+        pose = res._poses[0]
+        bbox_t = np.array(list(pose.bbox_t), int)
+        if pose.status == -2:
+            return np.zeros((1)), -1, -1, -1, -1, bbox_t                      # :79
+        if pose.status != 1:
+            if pose.n_cand <= 0:
+                return self._fetch_pred(1, 0, False), -1, -1, -1, -1, bbox_t   # :125-127
+            return self._fetch_pred(2, pose.cand_base + pose.n_cand - 1, True), -1, -1, -1, -1, bbox_t   # :189-191
+        xyz, mask, bx = self._fetch_crop(0, pose)
+        valid_mask_full = np.zeros((rgb.shape[0], rgb.shape[1]), bool)
+        valid_mask_full[bx[4]:bx[5], bx[6]:bx[7]] = mask
+        return (xyz, valid_mask_full, np.array(list(pose.R)).reshape(3, 3), np.array(list(pose.t)), pose.frac_inlier,
+                bbox_t)                                                        # :193
+
+    def pnp_ransac(self, rgb_aug_test, img_prob_ori, non_zero, v1, v2, u1, u2):
+        """recognition.py:195-224 with the PnP itself on the GPU (host-side correspondence build:
+        this standalone entry point takes host arrays, as the reference's does)."""
+        xyz = rgb_aug_test[v1:v2, u1:u2].astype(np.float64) / 255 * 2 - 1
+        for a in range(3):
+            xyz[:, :, a] = xyz[:, :, a] * self.obj_scale[a] + self.obj_ct[a]
+        valid_mask = np.logical_and(non_zero, img_prob_ori < self.th_i)
+        vs, us = np.where(valid_mask == 1)
+        n_pts = len(vs)
+        if n_pts < 6:
+            return np.eye(3), np.array([0, 0, 0]), valid_mask, -1
+        img_pts = np.stack((us + u1, vs + v1), axis=1).astype(np.float64)
+        ret, rvec, tvec, inliers, R, _ = solve_pnp_ransac(xyz[vs, us], img_pts, self.camK, 5.0, 100, 0.99)
+        if inliers is None:
+            return np.eye(3), np.array([0, 0, 0]), -1, -1
+        return R, tvec[:, 0], valid_mask, len(inliers)

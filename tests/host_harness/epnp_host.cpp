@@ -38,3 +38,75 @@ void host_eig12(const double* A, double* Vt, double* w) {
     epnp::jacobi_eig_sym<12>(B, Vt, w);
 }
 }
+
+// ---- CPU emulation of csrc/pnp_ransac.cu built from the same __host__ __device__ functions
+// (test infrastructure: lets the RANSAC semantics be checked against cv2.solvePnPRansac without a GPU).
+#include <vector>
+static float reproj_err_host(const double* R, const double* t, const float* o, const float* ip, const double* cam) {
+    const double X = o[0], Y = o[1], Z = o[2];
+    double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+    double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+    double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    z = z != 0.0 ? 1.0 / z : 1.0;
+    x *= z; y *= z;
+    const float u = (float)(x * cam[0] + cam[2]), v = (float)(y * cam[1] + cam[3]);
+    volatile float dx = ip[0] - u, dy = ip[1] - v;
+    volatile float a = dx * dx, b = dy * dy;
+    return a + b;
+}
+
+extern "C" int host_ransac(const double* obj64, const double* img64, int n, const double* cam4, float thr, int iters,
+                           double conf, double* rvec, double* tvec, unsigned char* mask, int* iters_run) {
+    std::vector<float> o(n * 3), ip(n * 2);
+    for (int i = 0; i < n * 3; ++i) o[i] = (float)obj64[i];
+    for (int i = 0; i < n * 2; ++i) ip[i] = (float)img64[i];
+    epnp::Cam cam = {cam4[0], cam4[1], cam4[2], cam4[3]};
+    const float thr2 = (float)((double)thr * (double)thr);
+    CvRng rng;
+    std::vector<double> hyp(iters * 12);
+    std::vector<int> counts(iters);
+    for (int h = 0; h < iters; ++h) {
+        int idx[5];
+        ransac_subset5(rng, n, idx);
+        double pws[15], us[10];
+        for (int j = 0; j < 5; ++j) {
+            for (int k = 0; k < 3; ++k) pws[3 * j + k] = o[idx[j] * 3 + k];
+            const float xn = (float)(((double)ip[idx[j] * 2] - cam.uc) * (1.0 / cam.fu));
+            const float yn = (float)(((double)ip[idx[j] * 2 + 1] - cam.vc) * (1.0 / cam.fv));
+            us[2 * j] = (double)xn * cam.fu + cam.uc;
+            us[2 * j + 1] = (double)yn * cam.fv + cam.vc;
+        }
+        double R[3][3], t[3], rv[3];
+        epnp::solve_small<5>(pws, us, 5, cam, R, t);
+        epnp::rodrigues_to_vec(R, rv);
+        epnp::rodrigues_to_mat(rv, R);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) hyp[h * 12 + i * 3 + j] = R[i][j];
+        for (int i = 0; i < 3; ++i) hyp[h * 12 + 9 + i] = t[i];
+        int c = 0;
+        for (int i = 0; i < n; ++i) c += reproj_err_host(&hyp[h * 12], &hyp[h * 12 + 9], &o[3 * i], &ip[2 * i], cam4) <= thr2;
+        counts[h] = c;
+    }
+    int max_good = 0, niters = iters > 1 ? iters : 1, best = -1, it = 0;
+    for (; it < niters; ++it) {
+        if (counts[it] > (max_good > 4 ? max_good : 4)) {
+            best = it; max_good = counts[it];
+            niters = ransac_update_num_iters(conf, (double)(n - max_good) / n, 5, niters);
+        }
+    }
+    *iters_run = it;
+    if (best < 0) return -1;
+    std::vector<double> pw, uv;
+    for (int i = 0; i < n; ++i) {
+        mask[i] = reproj_err_host(&hyp[best * 12], &hyp[best * 12 + 9], &o[3 * i], &ip[2 * i], cam4) <= thr2;
+        if (mask[i]) {
+            for (int k = 0; k < 3; ++k) pw.push_back(o[3 * i + k]);
+            uv.push_back(ip[2 * i]); uv.push_back(ip[2 * i + 1]);
+        }
+    }
+    double R[3][3];
+    static thread_local std::vector<char> big;  // solve_small keeps n-sized scratch on the stack
+    epnp::solve_small<20000>(pw.data(), uv.data(), (int)(pw.size() / 3), cam, R, tvec);
+    epnp::rodrigues_to_vec(R, rvec);
+    return max_good;
+}
