@@ -41,6 +41,10 @@ typedef struct p2p_model p2p_model_t;   /* per object: packed weights (reference
 P2P_API const char* p2p_last_error(void);
 P2P_API const char* p2p_version(void);
 
+/* Selects the CUDA device for the calling thread's subsequent p2p_* calls (one process per GPU:
+ * pass LOCAL_RANK).  The library links its own CUDA runtime, so torch.cuda.set_device does not reach it. */
+P2P_API int p2p_set_device(int device);
+
 /* Number of fp32 values in a weight blob for `backbone` ("resnet50" | "paper"): all tensors of
  * pix2pose_b200/weights.py:param_names(backbone), Keras layouts, concatenated in that order
  * (= the order Model.load_weights walks an inference*.hdf5, recognition.py:23-26). 0 on error. */
@@ -131,6 +135,15 @@ P2P_API long long p2p_pipeline_launch_count(const p2p_pipeline_t* p);
  * the mean.  Inputs stay in HBM: this is the kernel-only number (bench.py `value`). */
 P2P_API int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,
                      float* ms_per_iter);
+/* Measurement: CUDA events on the engine's stream (the stream every kernel of the engine / pipeline is
+ * launched on). slot in [0,8). p2p_engine_event_elapsed synchronises on slot_b. */
+P2P_API int p2p_engine_event_record(p2p_engine_t* e, int slot);
+P2P_API int p2p_engine_event_elapsed(p2p_engine_t* e, int slot_a, int slot_b, float* ms);
+/* Measurement: one forward of n <= capacity crops with every launch bracketed by CUDA events;
+ * ms[0] = summed duration of the tcgen05 conv launches, ms[1] = other kernels, counts[0..1] likewise. */
+P2P_API int p2p_engine_profile_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, double* ms, int* counts);
+/* Copies frames to a pipeline-owned device buffer (for p2p_pipeline_run_device); *dev receives the pointer. */
+P2P_API int p2p_pipeline_upload_frames(p2p_pipeline_t* p, const uint8_t* frames, int F, int H, int W, void** dev);
 /* Page-locked host buffers for the end-to-end path (bench.py `e2e`). */
 P2P_API void* p2p_host_alloc(size_t bytes);
 P2P_API void p2p_host_free(void* p);

@@ -45,6 +45,7 @@ def lib():
     sig = {
         "p2p_last_error": (ctypes.c_char_p, []),
         "p2p_version": (ctypes.c_char_p, []),
+        "p2p_set_device": (ctypes.c_int, [ctypes.c_int]),
         "p2p_param_count": (ctypes.c_size_t, [ctypes.c_char_p]),
         "p2p_flops_per_crop": (ctypes.c_double, [ctypes.c_char_p]),
         "p2p_engine_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
@@ -69,6 +70,11 @@ def lib():
         "p2p_pipeline_debug_override": (ctypes.c_int, [vp, ctypes.c_int, c_f, c_f, ctypes.c_int]),
         "p2p_pipeline_launch_count": (ctypes.c_longlong, [vp]),
         "p2p_time_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_engine_event_record": (ctypes.c_int, [vp, ctypes.c_int]),
+        "p2p_engine_event_elapsed": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_engine_profile_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, c_d, c_i]),
+        "p2p_pipeline_upload_frames": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.POINTER(vp)]),
         "p2p_host_alloc": (vp, [ctypes.c_size_t]),
         "p2p_host_free": (None, [vp]),
         "p2p_engine_read_tensor": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int, c_f, c_i, c_i, c_i]),

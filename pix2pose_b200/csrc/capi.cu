@@ -18,6 +18,16 @@ extern "C" {
 const char* p2p_last_error(void) { return get_last_error(); }
 const char* p2p_version(void) { return "pix2pose_b200 0.1 (sm_100a)"; }
 
+int p2p_set_device(int device) {
+    return guarded([&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw Error(P2P_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+        P2P_CHECK(device >= 0 && device < count, "device %d outside [0,%d)", device, count);
+        P2P_CUDA(cudaSetDevice(device));
+    });
+}
+
 size_t p2p_param_count(const char* backbone) {
     size_t n = 0;
     guarded([&] { n = param_count(parse_backbone(backbone)); });
@@ -169,6 +179,51 @@ int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int 
         cudaEventDestroy(a);
         cudaEventDestroy(b);
         *ms_per_iter = ms / iters;
+    });
+}
+
+int p2p_engine_event_record(p2p_engine_t* e, int slot) {
+    return guarded([&] {
+        P2P_CHECK(e && slot >= 0 && slot < 8, "bad argument");
+        Engine& E = *e->e;
+        if (!E.ev[slot]) P2P_CUDA(cudaEventCreate(&E.ev[slot]));
+        P2P_CUDA(cudaEventRecord(E.ev[slot], E.stream));
+    });
+}
+int p2p_engine_event_elapsed(p2p_engine_t* e, int slot_a, int slot_b, float* ms) {
+    return guarded([&] {
+        P2P_CHECK(e && ms && slot_a >= 0 && slot_a < 8 && slot_b >= 0 && slot_b < 8, "bad argument");
+        Engine& E = *e->e;
+        P2P_CHECK(E.ev[slot_a] && E.ev[slot_b], "event slot not recorded");
+        P2P_CUDA(cudaEventSynchronize(E.ev[slot_b]));
+        P2P_CUDA(cudaEventElapsedTime(ms, E.ev[slot_a], E.ev[slot_b]));
+    });
+}
+int p2p_engine_profile_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, double* ms, int* counts) {
+    return guarded([&] {
+        P2P_CHECK(e && m && x && ms && counts, "NULL argument");
+        Engine& E = *e->e;
+        P2P_CHECK(n >= 1 && n <= E.cap, "n=%d outside [1,%d]", n, E.cap);
+        P2P_CUDA(cudaMemcpyAsync(E.x.p, x, static_cast<size_t>(n) * 128 * 128 * 3 * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+        for (int i = 0; i < 2; ++i) E.forward(*m->m, E.x.p, n, E.dec.p, E.prob.p, nullptr, E.stream);
+        double prof[4] = {0, 0, 0, 0};
+        E.prof = prof;
+        try {
+            E.forward(*m->m, E.x.p, n, E.dec.p, E.prob.p, nullptr, E.stream);
+        } catch (...) {
+            E.prof = nullptr;
+            throw;
+        }
+        E.prof = nullptr;
+        ms[0] = prof[0]; ms[1] = prof[1];
+        counts[0] = static_cast<int>(prof[2]); counts[1] = static_cast<int>(prof[3]);
+    });
+}
+int p2p_pipeline_upload_frames(p2p_pipeline_t* p, const uint8_t* frames, int F, int H, int W, void** dev) {
+    return guarded([&] {
+        P2P_CHECK(p && frames && dev, "NULL argument");
+        *dev = const_cast<uint8_t*>(p->p->upload_frames(frames, F, H, W));
+        P2P_CUDA(cudaStreamSynchronize(p->p->engine->stream));
     });
 }
 

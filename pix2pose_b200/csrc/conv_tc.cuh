@@ -51,6 +51,12 @@ struct ConvParams {
     float* out_dec;   // ACT_HEADS: (N,OH,OW,3) fp32 tanh
     float* out_prob;  // ACT_HEADS: (N,OH,OW,1) fp32 sigmoid
     const int* n_active;  // optional device-side count of live images (tiles past it exit)
+    // split-K (Dense layers with a tiny M x N grid): blockIdx.z = K slice of `splitk_chunk` k-iterations; the raw
+    // fp32 accumulators go to out_partial[z][row][Cout_pad] and splitk_reduce_kernel finishes the layer.
+    int splitk_chunk;
+    float* out_partial;
+    long long partial_stride;  // elements between K slices
+    int Cout_pad;
 };
 
 template <int BN, int NP>
@@ -101,8 +107,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const int n0 = tn * p.nb, y0 = ty * p.th, x0 = tx * p.tw;
     if (n0 >= n_limit) return;
     const int nt0 = blockIdx.y * BN;
-    const int kbeg = p.kstart[z];
-    const int nk = p.kstart[z + 1] - kbeg;
+    const bool splitk = p.splitk_chunk > 0;
+    const int zi = splitk ? 0 : z;  // index into the per-phase tables
+    const int kbeg = splitk ? z * p.splitk_chunk : p.kstart[z];
+    const int nk = splitk ? min(p.splitk_chunk, p.kstart[1] - kbeg) : p.kstart[z + 1] - kbeg;
 
     // ---- shared memory carve-up (1024-B aligned operand tiles for the 128-B swizzle)
     extern __shared__ uint8_t smem_raw[];
@@ -187,11 +195,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         const int nl = r / (p.tw * p.th);
         const int y = y0 + hl, x = x0 + wl, n = n0 + nl;
         const bool valid = (y < p.H) && (x < p.W) && (n < n_limit);
-        const int oy = y * p.sy + p.oy_off[z], ox = x * p.sx + p.ox_off[z];
+        const int oy = y * p.sy + p.oy_off[zi], ox = x * p.sx + p.ox_off[zi];
         const long long pix = (static_cast<long long>(n) * p.OH + oy) * p.OW + ox;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
         if (p.act == ACT_HEADS) {
+            // Phase-fused transposed-conv heads: the 16 accumulator columns are (output phase a,b) x (x,y,z,prob);
+            // this row's input pixel (y,x) produces the 2x2 output pixels (2y+a, 2x+b).
             uint32_t v[16];
             tmem_ld_32x16(taddr, v);
             tmem_ld_wait();
@@ -201,16 +211,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                 tmem_ld_32x16(taddr + 2 * Cfg::ACC_STRIDE, v2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 16; ++j)
                     v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(v1[j])) + __uint_as_float(v2[j]));
             }
             if (valid) {
-                float* d = p.out_dec + pix * 3;
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    d[c] = tanhf(__uint_as_float(v[c]) * __ldg(&p.scale[c]) + __ldg(&p.shift[c]));
-                const float e = __uint_as_float(v[3]) * __ldg(&p.scale[3]) + __ldg(&p.shift[3]);
-                p.out_prob[pix] = 1.f / (1.f + expf(-e));
+                for (int ph = 0; ph < 4; ++ph) {
+                    const long long opix = (static_cast<long long>(n) * p.OH + (2 * y + (ph >> 1))) * p.OW + (2 * x + (ph & 1));
+                    float* d = p.out_dec + opix * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        d[c] = tanhf(__uint_as_float(v[ph * 4 + c]) * __ldg(&p.scale[ph * 4 + c]) + __ldg(&p.shift[ph * 4 + c]));
+                    const float e = __uint_as_float(v[ph * 4 + 3]) * __ldg(&p.scale[ph * 4 + 3]) + __ldg(&p.shift[ph * 4 + 3]);
+                    p.out_prob[opix] = 1.f / (1.f + expf(-e));
+                }
             }
         } else {
             constexpr int NCH = BN >= 32 ? BN / 32 : 1;
@@ -231,7 +245,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
                 }
                 const int c0 = nt0 + ch * 32;
-                if (valid && c0 < p.Cout) {
+                if (splitk) {
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(p.out_partial + z * p.partial_stride + pix * p.Cout_pad + c0);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                                 __uint_as_float(v[4 * g + 3]));
+                    }
+                } else if (valid && c0 < p.Cout) {
                     __half* o_hi = p.out_hi + pix * p.Ctot + p.c_off + c0;
                     const __half* r_hi = p.res_hi ? p.res_hi + pix * p.res_Ctot + c0 : nullptr;
 #pragma unroll
@@ -267,6 +289,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// Finishes a split-K layer: out[row][c] = act((sum_z partial[z][row][c]) * scale[c] + shift[c]) -> fp16 hi/lo planes.
+static __global__ void splitk_reduce_kernel(const float* __restrict__ partial, long long partial_stride, int nsplit, int rows,
+                                     int Cout, int Cout_pad, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int act, __half* __restrict__ out_hi, long long out_plane, int Ctot,
+                                     const int* __restrict__ n_active) {
+    int n_limit = rows;
+    if (n_active) n_limit = min(n_limit, *n_active);
+    const long long total = static_cast<long long>(n_limit) * Cout;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cout);
+        const long long r = i / Cout;
+        float acc = 0.f;
+        for (int z = 0; z < nsplit; ++z) acc += partial[z * partial_stride + r * Cout_pad + c];
+        const float v = act_apply(acc * scale[c] + shift[c], act);
+        const __half h = __float2half_rn(v);
+        out_hi[r * Ctot + c] = h;
+        if (out_plane) out_hi[r * Ctot + c + out_plane] = __float2half_rn(v - __half2float(h));
+    }
 }
 
 }  // namespace p2p

@@ -174,7 +174,7 @@ struct PlanBuilder {
         const int d3 = T("d3", 64, 64, 64), d3u = T("d3_uni", 64, 64, 128);
         conv("convT3", K_CONVT, 5, {all(d2u)}, {{"convT3", "bn_convT3"}}, d3, ACT_LRELU);
         conv("deconv3", K_CONV, 5, {all(d3), s1}, {{"deconv3", "bn_deconv3"}}, d3u, ACT_LRELU);
-        conv("heads", K_CONVT, 5, {all(d3u)}, {{"convT_xyz", ""}, {"convT_prob", ""}}, -1, ACT_HEADS);
+        conv("heads", K_CONVT_FUSED, 5, {all(d3u)}, {{"convT_xyz", ""}, {"convT_prob", ""}}, -1, ACT_HEADS);
     }
 };
 
@@ -262,6 +262,20 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
                         }
                 c.kstart[z + 1] = static_cast<int>(c.kit.size());
             }
+    } else if (c.kind == K_CONVT_FUSED) {
+        // All four output phases in one GEMM: N = 4 phases x Cout (tiny heads), K = 3x3 input neighbourhood.
+        // Phase a (output row parity) uses kernel row kh(a,dy): a=0: dy=0->1, dy=-1->3 ; a=1: dy=+1->0, dy=0->2, dy=-1->4.
+        c.H = t0.H; c.W = t0.W; c.sy = c.sx = 2;
+        const SrcSpec& s = c.srcs[0];
+        c.maps.push_back({s.tensor, 0, s.c_begin + s.c_count});
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int ch = 0; ch < chunks(s.c_count); ++ch) {
+                    c.kit.push_back(make_int4(0, dy, dx, s.c_begin + ch * 64));
+                    c.kw.push_back({dy, dx, ch * 64, std::min(64, s.c_count - ch * 64)});
+                }
+        c.kstart[1] = static_cast<int>(c.kit.size());
+        c.Cout *= 4;   // accumulator columns
     } else if (c.kind == K_DENSE) {
         c.H = 1; c.W = 1;
         const SrcSpec& s = c.srcs[0];
@@ -273,6 +287,11 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
             c.kw.push_back({0, 0, ch * 64, 64});
         }
         c.kstart[1] = static_cast<int>(c.kit.size());
+    }
+    if (c.kind == K_CONVT_FUSED) { c.BN = 16; c.Cout_pad = 16; }
+    if (c.kind == K_DENSE && c.kit.size() >= 64) {  // dense_1: K = 32768 -> 32 slices of 16 k-iterations
+        c.splitk_chunk = 16;
+        c.splitk = static_cast<int>((c.kit.size() + c.splitk_chunk - 1) / c.splitk_chunk);
     }
     if (c.phases == 1)
         for (int z = 1; z < 5; ++z) c.kstart[z] = c.kstart[1];
@@ -396,6 +415,12 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     dec.alloc(static_cast<size_t>(cap) * 128 * 128 * 3);
     prob.alloc(static_cast<size_t>(cap) * 128 * 128);
 
+    {
+        size_t need = 0;
+        for (auto& c : plan.convs)
+            if (c.splitk > 1) need = std::max(need, static_cast<size_t>(c.splitk) * cap * c.Cout_pad);
+        if (need) partial.alloc(need);
+    }
     conv_rt.resize(plan.convs.size());
     for (size_t ci = 0; ci < plan.convs.size(); ++ci) {
         const ConvSpec& c = plan.convs[ci];
@@ -431,6 +456,8 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
 }
 
 Engine::~Engine() {
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -469,7 +496,36 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
         const float wscale = wmax > 0.f ? exp2f(floorf(log2f(128.f / wmax))) : 1.f;
         const size_t KI = c.kit.size();
         std::vector<__half> packed(KI * np * c.Cout_pad * 64, __float2half(0.f));
-        for (size_t it = 0; it < KI; ++it) {
+        if (c.kind == K_CONVT_FUSED) {
+            const int khmap[2][3] = {{3, 1, -1}, {4, 2, 0}};  // [phase parity][d + 1] -> kernel index (or -1)
+            int tot = 0;
+            for (auto& q : pw) tot += q.cout;
+            P2P_CHECK(tot * 4 <= c.Cout_pad, "fused transposed conv: too many output channels");
+            for (size_t it = 0; it < KI; ++it) {
+                const KWeight& kw = c.kw[it];
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int kh = khmap[ph >> 1][kw.kh + 1], kwi = khmap[ph & 1][kw.kw + 1];
+                    if (kh < 0 || kwi < 0) continue;
+                    int ch_base = 0;
+                    for (auto& q : pw) {
+                        const LayerDef& l = *q.l;
+                        for (int co = 0; co < q.cout; ++co) {
+                            const int n = ph * tot + ch_base + co;
+                            for (int j = 0; j < kw.nvalid; ++j) {
+                                const int cin = kw.cin_begin + j;
+                                const float v = q.k[((static_cast<size_t>(kh) * 5 + kwi) * l.shape[2] + co) * l.shape[3] + cin] * wscale;
+                                const __half h = __float2half_rn(v);
+                                const size_t o = ((it * np + 0) * c.Cout_pad + n) * 64 + j;
+                                packed[o] = h;
+                                if (np == 2) packed[o + static_cast<size_t>(c.Cout_pad) * 64] = __float2half_rn(v - __half2float(h));
+                            }
+                        }
+                        ch_base += q.cout;
+                    }
+                }
+            }
+        }
+        for (size_t it = 0; c.kind != K_CONVT_FUSED && it < KI; ++it) {
             const KWeight& kw = c.kw[it];
             int n_base = 0;
             for (auto& q : pw) {
@@ -501,7 +557,19 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
         }
         std::vector<float> sc(c.Cout_pad, 0.f), sh(c.Cout_pad, 0.f);
         int n_base = 0;
+        if (c.kind == K_CONVT_FUSED) {
+            int tot = 0;
+            for (auto& q : pw) tot += q.cout;
+            for (int ph = 0; ph < 4; ++ph) {
+                int cb = 0;
+                for (auto& q : pw) {
+                    for (int co = 0; co < q.cout; ++co) { sc[ph * tot + cb + co] = 1.f / wscale; sh[ph * tot + cb + co] = q.b[co]; }
+                    cb += q.cout;
+                }
+            }
+        }
         for (auto& q : pw) {
+            if (c.kind == K_CONVT_FUSED) break;
             for (int co = 0; co < q.cout; ++co) {
                 float s = 1.f, t = q.b[co];
                 if (q.bn) {
@@ -547,6 +615,17 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                      cudaStream_t s) {
     P2P_CHECK(n >= 1 && n <= cap, "forward: n=%d outside [1,%d]", n, cap);
     P2P_CHECK(m.engine == this, "model was packed for a different engine");
+    std::vector<cudaEvent_t> pev;
+    std::vector<int> pkind;
+    auto mark = [&](int kind) {
+        if (!prof) return;
+        cudaEvent_t e;
+        P2P_CUDA(cudaEventCreate(&e));
+        P2P_CUDA(cudaEventRecord(e, s));
+        pev.push_back(e);
+        pkind.push_back(kind);
+    };
+    mark(-1);
     for (const Step& st : plan.steps) {
         if (st.kind == S_IM2COL) {
             const long long total = static_cast<long long>(n) * 64 * 64 * st.d;
@@ -554,6 +633,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             im2col_stem_kernel<<<blocks, 256, 0, s>>>(x_dev, tensors[st.a].buf.p, tensors[st.a].plane, n, st.b, st.c, st.d, n_active);
             P2P_CUDA(cudaGetLastError());
             ++launches;
+            mark(1);
         } else if (st.kind == S_MAXPOOL) {
             const TensorSpec& ti = plan.tensors[st.a];
             const long long total = static_cast<long long>(n) * (ti.H / 2) * (ti.W / 2) * ti.C;
@@ -562,6 +642,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                                                        tensors[st.b].plane, n, ti.H, ti.W, ti.C, n_active);
             P2P_CUDA(cudaGetLastError());
             ++launches;
+            mark(1);
         } else {
             const ConvSpec& c = plan.convs[st.a];
             const ConvRt& rt = conv_rt[st.a];
@@ -590,8 +671,14 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 p.res_Ctot = plan.tensors[c.res_tensor].C;
             }
             p.n_active = n_active;
+            p.Cout_pad = c.Cout_pad;
+            if (c.splitk > 1) {
+                p.splitk_chunk = c.splitk_chunk;
+                p.out_partial = partial.p;
+                p.partial_stride = static_cast<long long>(cap) * c.Cout_pad;
+            }
             const int tiles_n = (n + c.nb - 1) / c.nb;
-            dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.phases);
+            dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             if (np == 2) {
                 if (c.BN == 128) launch_conv<128, 2>(rt.mapA, mc.mapB, p, grid, s);
                 else if (c.BN == 64) launch_conv<64, 2>(rt.mapA, mc.mapB, p, grid, s);
@@ -602,7 +689,28 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 else launch_conv<16, 1>(rt.mapA, mc.mapB, p, grid, s);
             }
             ++launches;
+            mark(0);
+            if (c.splitk > 1) {
+                const TensorSpec& to = plan.tensors[c.out_tensor];
+                const long long total = static_cast<long long>(n) * c.Cout;
+                const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, num_sms * 8));
+                splitk_reduce_kernel<<<blocks, 256, 0, s>>>(partial.p, p.partial_stride, c.splitk, n, c.Cout, c.Cout_pad, mc.scale.p,
+                                                            mc.shift.p, c.act, p.out_hi, p.out_plane, to.H * to.W * to.C, n_active);
+                P2P_CUDA(cudaGetLastError());
+                ++launches;
+                mark(1);
+            }
         }
+    }
+    if (prof) {
+        P2P_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 1; i < pev.size(); ++i) {
+            float ms = 0;
+            P2P_CUDA(cudaEventElapsedTime(&ms, pev[i - 1], pev[i]));
+            prof[pkind[i]] += ms;
+            prof[2 + pkind[i]] += 1;
+        }
+        for (auto e : pev) cudaEventDestroy(e);
     }
 }
 

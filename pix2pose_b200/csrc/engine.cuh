@@ -28,7 +28,7 @@ std::vector<LayerDef> layer_table(int backbone);
 size_t param_count(int backbone);
 int parse_backbone(const char* s);
 
-enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4 };
+enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4, K_CONVT_FUSED = 5 };
 
 struct SrcSpec { int tensor, c_begin, c_count; };
 struct WPart { std::string layer, bn; };
@@ -45,6 +45,7 @@ struct ConvSpec {
     int H = 0, W = 0, tw = 0, th = 0, nb = 0, phases = 1;
     int Cin = 0, Cout = 0, Cout_pad = 0, BN = 0;
     int kstart[5] = {0, 0, 0, 0, 0};
+    int splitk = 1, splitk_chunk = 0;  // K slices (Dense layers whose M x N grid cannot fill the GPU)
     int oy_off[4] = {0, 0, 0, 0}, ox_off[4] = {0, 0, 0, 0}, sy = 1, sx = 1;
     std::vector<int4> kit;
     std::vector<KWeight> kw;
@@ -92,6 +93,7 @@ class Engine {
     struct Tensor { DevBuf<__half> buf; long long plane = 0; };
     std::vector<Tensor> tensors;
     DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
+    DevBuf<float> partial;       // split-K scratch [slices][cap][Cout_pad]
     struct ConvRt { DevBuf<int4> kit; CUtensorMap mapA[4]; };
     std::vector<ConvRt> conv_rt;
     int num_sms = 148;
@@ -103,6 +105,10 @@ class Engine {
     void predict_host(const Model& m, const float* x, int n, float* dec, float* prob);
     void read_tensor(const std::string& name, int n, float* out);  // debug: activation (n,H,W,C) as fp32
     long long launches = 0;  // kernels launched so far (for bench's gpu_launches)
+    // Measurement: when `prof` is set, forward() brackets every launch with CUDA events on its stream and
+    // adds the elapsed times (ms) to prof[0] (tcgen05 conv kernels) / prof[1] (other kernels); counts in prof[2..3].
+    double* prof = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // user timing slots
 };
 
 }  // namespace p2p

@@ -32,6 +32,10 @@ def init(backend=None):
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     elif world == 1 and torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
+    if torch.cuda.is_available():
+        # the C library links its own CUDA runtime: point it at this rank's GPU as well
+        from . import _lib
+        _lib.check(_lib.lib().p2p_set_device(local_rank))
     return rank, local_rank, world
 
 

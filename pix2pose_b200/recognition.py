@@ -167,33 +167,55 @@ class pix2pose():
             d.ct[:] = [float(v) for v in self.obj_ct]
         return dets
 
-    def est_pose_batch(self, frames, bboxes, frame_ids=None, camKs=None):
+    def est_pose_batch(self, frames, bboxes, frame_ids=None, camKs=None, frames_dev=None):
         """Poses for many detections of this object in one device pipeline run.
 
         frames: (F,H,W,3) uint8 (or a single (H,W,3) image); bboxes: (n,4) rois [v0,u0,v1,u1];
         frame_ids: (n,) index of each roi's frame (default 0); camKs: optional per-detection intrinsics.
         Returns a ``PoseBatchResult``; ``status``: 1 pose found, 0 the reference would return its -1
         sentinels, -2 the crop was smaller than 5 px (recognition.py:78)."""
-        frames = np.asarray(frames)
-        if frames.ndim == 3:
-            frames = frames[None]
-        if frames.dtype != np.uint8:
-            # the ICP driver passes float32 images holding 0..255 (5_evaluation_bop_icp3d.py:369)
-            frames = frames.astype(np.uint8)
-        frames = np.ascontiguousarray(frames)
-        F, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
         n = len(bboxes)
+        if frames_dev is not None:
+            dev, F, H, W, pipe0 = frames_dev
+        else:
+            frames = np.asarray(frames)
+            if frames.ndim == 3:
+                frames = frames[None]
+            if frames.dtype != np.uint8:
+                # the ICP driver passes float32 images holding 0..255 (5_evaluation_bop_icp3d.py:369)
+                frames = frames.astype(np.uint8)
+            frames = np.ascontiguousarray(frames)
+            F, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
         if frame_ids is None:
             frame_ids = np.zeros(n, np.int64)
         dets = self._make_dets((H, W), bboxes, frame_ids, camKs)
         poses = (_Pose * max(n, 1))()
         th = np.ascontiguousarray(np.asarray(self.th_o, np.float64))
         pipe = self._pipeline(n)
-        _lib.check(_lib.lib().p2p_pipeline_run(
-            pipe, self.generator_train._model, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), F, H, W, dets, n,
-            th.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(self.th_i), 5.0, 100, 0.99, poses))
+        thp = th.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if frames_dev is not None:
+            if pipe0 is not pipe:
+                raise RuntimeError("frames_dev belongs to a pipeline that was rebuilt; upload the frames again")
+            _lib.check(_lib.lib().p2p_pipeline_run_device(pipe, self.generator_train._model, dev, F, H, W, dets, n, thp,
+                                                          float(self.th_i), 5.0, 100, 0.99, poses))
+        else:
+            _lib.check(_lib.lib().p2p_pipeline_run(
+                pipe, self.generator_train._model, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), F, H, W, dets, n,
+                thp, float(self.th_i), 5.0, 100, 0.99, poses))
         self._last = (dets, poses, n, (H, W))
         return PoseBatchResult(self, poses, n)
+
+    def upload_frames(self, frames, n_dets=1):
+        """Copies (F,H,W,3) uint8 frames into the pipeline's device buffer; returns an opaque handle for
+        ``est_pose_batch(..., frames_dev=handle)`` (keeps detector output on the device)."""
+        frames = np.ascontiguousarray(np.asarray(frames, np.uint8))
+        if frames.ndim == 3:
+            frames = frames[None]
+        pipe = self._pipeline(n_dets)
+        dev = ctypes.c_void_p()
+        _lib.check(_lib.lib().p2p_pipeline_upload_frames(pipe, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                                         frames.shape[0], frames.shape[1], frames.shape[2], ctypes.byref(dev)))
+        return (dev, frames.shape[0], frames.shape[1], frames.shape[2], pipe)
 
     def _fetch_crop(self, d, pose):
         bx = list(pose.best_box)

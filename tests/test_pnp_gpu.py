@@ -49,8 +49,9 @@ def test_matches_cv2_on_planted_poses():
         Rcv = cv2.Rodrigues(rv)[0]
         ang = np.degrees(np.arccos(np.clip((np.trace(Rcv.T @ g_R) - 1) / 2, -1, 1)))
         dt = np.linalg.norm(g_tv - tv) / np.linalg.norm(tv)
-        if same:
-            assert ang < 1e-4 and dt < 1e-8                 # same inliers -> same refit
+        if same and len(inl) >= 12:
+            assert ang < 1e-4 and dt < 1e-8                 # same inliers -> same refit (a 5/6-point refit keeps the
+            #                                                 null-space ambiguity described above)
         if n >= 100:
             assert ang <= 0.6 and dt <= 5e-3, (trial, n, of, ang, dt)
             assert abs(len(inl) - len(g_inl)) <= 0.05 * n
