@@ -190,6 +190,10 @@ def run_ours(args):
         state["res"] = rec.est_pose_batch(None, rois, fids, frames_dev=fdev)
         state["all"] = gather(state["res"])
 
+    if args.profile:                      # short run for `ncu` launch lists: 1 warm-up + 1 step, no JSON
+        step_dev()
+        step_dev()
+        return
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = rec.launch_count
@@ -265,6 +269,7 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--capacity", type=int, default=256)
     ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--profile", action="store_true", help="one warm-up + one step only (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

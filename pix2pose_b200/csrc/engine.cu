@@ -628,7 +628,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
     mark(-1);
     for (const Step& st : plan.steps) {
         if (st.kind == S_IM2COL) {
-            const long long total = static_cast<long long>(n) * 64 * 64 * st.d;
+            const long long total = static_cast<long long>(n) * 64 * 64 * (st.d / 8);
             const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, num_sms * 16));
             im2col_stem_kernel<<<blocks, 256, 0, s>>>(x_dev, tensors[st.a].buf.p, tensors[st.a].plane, n, st.b, st.c, st.d, n_active);
             P2P_CUDA(cudaGetLastError());
@@ -636,7 +636,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             mark(1);
         } else if (st.kind == S_MAXPOOL) {
             const TensorSpec& ti = plan.tensors[st.a];
-            const long long total = static_cast<long long>(n) * (ti.H / 2) * (ti.W / 2) * ti.C;
+            const long long total = static_cast<long long>(n) * (ti.H / 2) * (ti.W / 2) * (ti.C / 8);
             const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, num_sms * 16));
             maxpool3x3s2_kernel<<<blocks, 256, 0, s>>>(tensors[st.a].buf.p, tensors[st.a].plane, tensors[st.b].buf.p,
                                                        tensors[st.b].plane, n, ti.H, ti.W, ti.C, n_active);

@@ -7,65 +7,91 @@
 
 namespace p2p {
 
-__device__ __forceinline__ void split_store(__half* hi, long long plane, long long idx, float v) {
-    const __half h = __float2half_rn(v);
-    hi[idx] = h;
-    if (plane) hi[idx + plane] = __float2half_rn(v - __half2float(h));
-}
-
 // x: (N,128,128,3) fp32 NHWC.  patches: (N,64,64,Kpad) fp16 hi/lo, K index = (kh*ks + kw)*3 + c,
 // input row = 2*oy + kh - pad (zero outside), columns likewise; K >= ks*ks*3 is zero padding.
+// One thread produces 8 consecutive K entries (one 16-byte store per plane).
 __global__ void im2col_stem_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane,
                                    int N, int ks, int pad, int Kpad, const int* __restrict__ n_active) {
     int n_limit = N;
     if (n_active) n_limit = min(n_limit, *n_active);
-    const long long total = static_cast<long long>(n_limit) * 64 * 64 * Kpad;
+    const int kg = Kpad / 8;
+    const long long total = static_cast<long long>(n_limit) * 64 * 64 * kg;
     const int kreal = ks * ks * 3;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(i % Kpad);
-        const long long pix = i / Kpad;
+        const int k0 = static_cast<int>(i % kg) * 8;
+        const long long pix = i / kg;
         const int ox = static_cast<int>(pix & 63), oy = static_cast<int>((pix >> 6) & 63);
         const int n = static_cast<int>(pix >> 12);
-        float v = 0.f;
-        if (k < kreal) {
-            const int c = k % 3, kw = (k / 3) % ks, kh = k / (3 * ks);
-            const int iy = 2 * oy + kh - pad, ix = 2 * ox + kw - pad;
-            if (iy >= 0 && iy < 128 && ix >= 0 && ix < 128) v = x[((static_cast<long long>(n) * 128 + iy) * 128 + ix) * 3 + c];
+        uint4 hi4, lo4;
+        __half* hh = reinterpret_cast<__half*>(&hi4);
+        __half* lh = reinterpret_cast<__half*>(&lo4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            float v = 0.f;
+            if (k < kreal) {
+                const int c = k % 3, kw = (k / 3) % ks, kh = k / (3 * ks);
+                const int iy = 2 * oy + kh - pad, ix = 2 * ox + kw - pad;
+                if (iy >= 0 && iy < 128 && ix >= 0 && ix < 128) v = __ldg(&x[((static_cast<long long>(n) * 128 + iy) * 128 + ix) * 3 + c]);
+            }
+            const __half h = __float2half_rn(v);
+            hh[j] = h;
+            lh[j] = __float2half_rn(v - __half2float(h));
         }
-        split_store(out, plane, i, v);
+        const long long o = pix * Kpad + k0;
+        *reinterpret_cast<uint4*>(out + o) = hi4;
+        if (plane) *reinterpret_cast<uint4*>(out + o + plane) = lo4;
     }
 }
 
 // MaxPooling2D(3x3, s2, 'same') on (N,64,64,64) -> (N,32,32,64): TF pads 0 before / 1 after with -inf.
+// One thread handles 8 channels (16-byte loads / stores per plane).
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, long long in_plane, __half* __restrict__ out,
                                     long long out_plane, int N, int H, int W, int C, const int* __restrict__ n_active) {
     int n_limit = N;
     if (n_active) n_limit = min(n_limit, *n_active);
-    const int OH = H / 2, OW = W / 2;
-    const long long total = static_cast<long long>(n_limit) * OH * OW * C;
+    const int OH = H / 2, OW = W / 2, cg = C / 8;
+    const long long total = static_cast<long long>(n_limit) * OH * OW * cg;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % C);
-        long long t = i / C;
+        const int c0 = static_cast<int>(i % cg) * 8;
+        long long t = i / cg;
         const int ox = static_cast<int>(t % OW);
         t /= OW;
         const int oy = static_cast<int>(t % OH);
         const int n = static_cast<int>(t / OH);
-        float m = -INFINITY;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
         for (int dy = 0; dy < 3; ++dy) {
             const int iy = 2 * oy + dy;
             if (iy >= H) continue;
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = 2 * ox + dx;
                 if (ix >= W) continue;
-                const long long j = ((static_cast<long long>(n) * H + iy) * W + ix) * C + c;
-                float v = __half2float(in[j]);
-                if (in_plane) v += __half2float(in[j + in_plane]);
-                m = fmaxf(m, v);
+                const long long j0 = ((static_cast<long long>(n) * H + iy) * W + ix) * C + c0;
+                const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(in + j0));
+                uint4 l4 = make_uint4(0, 0, 0, 0);
+                if (in_plane) l4 = __ldg(reinterpret_cast<const uint4*>(in + j0 + in_plane));
+                const __half* hh = reinterpret_cast<const __half*>(&h4);
+                const __half* lh = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __half2float(hh[j]) + __half2float(lh[j]));
             }
         }
-        split_store(out, out_plane, i, m);
+        uint4 oh, ol;
+        __half* ohh = reinterpret_cast<__half*>(&oh);
+        __half* olh = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const __half h = __float2half_rn(m[j]);
+            ohh[j] = h;
+            olh[j] = __float2half_rn(m[j] - __half2float(h));
+        }
+        const long long o = i * 8;
+        *reinterpret_cast<uint4*>(out + o) = oh;
+        if (out_plane) *reinterpret_cast<uint4*>(out + o + out_plane) = ol;
     }
 }
 

@@ -60,18 +60,48 @@ def _get_boxes(box_size, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
             cut_right + (hi_u - lo_u))
 
 
+DET_DTYPE = np.dtype([("frame", "<i4"), ("skip", "<i4"), ("bbox", "<i4", 4), ("box1", "<i4", 12), ("fu", "<f8"), ("fv", "<f8"),
+                      ("uc", "<f8"), ("vc", "<f8"), ("scale", "<f8", 3), ("ct", "<f8", 3), ("pool_off", "<i8"), ("cap_px", "<i4"),
+                      ("pad", "<i4")], align=True)
+POSE_DTYPE = np.dtype([("R", "<f8", 9), ("t", "<f8", 3), ("frac_inlier", "<f8"), ("status", "<i4"), ("n_inliers", "<i4"),
+                       ("best_cand", "<i4"), ("n_cand", "<i4"), ("bbox_t", "<i4", 4), ("best_box", "<i4", 12), ("n_init", "<i4"),
+                       ("mask_all_true", "<i4"), ("cand_base", "<i4"), ("pad", "<i4")], align=True)
+assert DET_DTYPE.itemsize == ctypes.sizeof(_Det) and POSE_DTYPE.itemsize == ctypes.sizeof(_Pose)
+
+
+def _get_boxes_batch(box_size, bboxes, v_max, u_max):
+    """Vectorised ``get_boxes`` (recognition.py:28-69) for integer rois without explicit centre: (n,12) int64.
+    Same arithmetic as the scalar version (float division, truncation toward zero)."""
+    b = np.asarray(bboxes, np.int64).reshape(-1, 4)
+    ct_v = np.trunc((b[:, 0] + b[:, 2]) / 2).astype(np.int64)
+    ct_u = np.trunc((b[:, 1] + b[:, 3]) / 2).astype(np.int64)
+    w = np.minimum(9999, np.maximum((b[:, 3] - b[:, 1]) * box_size, (b[:, 2] - b[:, 0]) * box_size))
+    half = np.trunc(w / 2).astype(np.int64)
+    lo_v, hi_v, lo_u, hi_u = ct_v - half, ct_v + half, ct_u - half, ct_u + half
+    out = np.empty((b.shape[0], 12), np.int64)
+    out[:, 0], out[:, 1], out[:, 2], out[:, 3] = lo_v, hi_v, lo_u, hi_u
+    out[:, 4], out[:, 5] = np.maximum(lo_v, 0), np.where(hi_v > v_max, v_max, hi_v)
+    out[:, 6], out[:, 7] = np.maximum(lo_u, 0), np.where(hi_u > u_max, u_max, hi_u)
+    out[:, 8] = np.where(lo_v < 0, -lo_v, 0)
+    out[:, 9] = np.where(hi_v > v_max, -(hi_v - v_max), 0) + (hi_v - lo_v)
+    out[:, 10] = np.where(lo_u < 0, -lo_u, 0)
+    out[:, 11] = np.where(hi_u > u_max, -(hi_u - u_max), 0) + (hi_u - lo_u)
+    return out
+
+
 class PoseBatchResult:
     """Result of ``est_pose_batch``: struct-of-arrays view plus lazy crop access."""
 
     def __init__(self, owner, poses, n):
         self._owner, self._poses, self.n = owner, poses, n
-        self.status = np.array([poses[i].status for i in range(n)], np.int32)
-        self.R = np.array([list(poses[i].R) for i in range(n)], np.float64).reshape(n, 3, 3)
-        self.t = np.array([list(poses[i].t) for i in range(n)], np.float64).reshape(n, 3)
-        self.n_inliers = np.array([poses[i].n_inliers for i in range(n)], np.int32)
-        self.frac_inlier = np.array([poses[i].frac_inlier for i in range(n)], np.float64)
-        self.bbox_t = np.array([list(poses[i].bbox_t) for i in range(n)], np.int64).reshape(n, 4)
-        self.n_cand = np.array([poses[i].n_cand for i in range(n)], np.int32)
+        a = np.frombuffer(poses, dtype=POSE_DTYPE, count=max(n, 1))[:n]
+        self.status = a["status"].copy()
+        self.R = a["R"].reshape(n, 3, 3).copy()
+        self.t = a["t"].copy()
+        self.n_inliers = a["n_inliers"].copy()
+        self.frac_inlier = a["frac_inlier"].copy()
+        self.bbox_t = a["bbox_t"].astype(np.int64)
+        self.n_cand = a["n_cand"].copy()
 
     def records(self):
         """(n, 16) float64 pose records for the multi-GPU gather: R9, t3, n_inliers, frac, status, index."""
@@ -151,20 +181,24 @@ class pix2pose():
         H, W = shape_hw
         n = len(bboxes)
         dets = (_Det * max(n, 1))()
-        for i in range(n):
-            bb = [int(v) for v in bboxes[i]]
-            box1 = self.get_boxes(bb, H, W)
-            d = dets[i]
-            d.frame = int(frame_ids[i])
-            d.bbox[:] = bb
-            d.box1[:] = [int(v) for v in box1]
-            side_v, side_u = box1[1] - box1[0], box1[3] - box1[2]
-            ph, pw = box1[5] - box1[4], box1[7] - box1[6]
-            d.skip = int(side_v < 5 or side_u < 5 or ph < 5 or pw < 5)   # recognition.py:78
-            K = np.asarray(camKs[i] if camKs is not None else self.camK, np.float64).reshape(3, 3)
-            d.fu, d.fv, d.uc, d.vc = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-            d.scale[:] = [float(v) for v in self.obj_scale]
-            d.ct[:] = [float(v) for v in self.obj_ct]
+        if n == 0:
+            return dets
+        a = np.frombuffer(dets, dtype=DET_DTYPE, count=n)
+        bb = np.array([[int(v) for v in b] for b in bboxes], np.int64).reshape(n, 4)
+        box1 = _get_boxes_batch(self.box_size, bb, H, W)
+        a["frame"] = np.asarray(frame_ids, np.int64)
+        a["bbox"] = bb
+        a["box1"] = box1
+        a["skip"] = ((box1[:, 1] - box1[:, 0] < 5) | (box1[:, 3] - box1[:, 2] < 5) | (box1[:, 5] - box1[:, 4] < 5) |
+                     (box1[:, 7] - box1[:, 6] < 5))                           # recognition.py:78
+        if camKs is None:
+            K = np.asarray(self.camK, np.float64).reshape(3, 3)
+            a["fu"], a["fv"], a["uc"], a["vc"] = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+        else:
+            Ks = np.asarray(camKs, np.float64).reshape(n, 3, 3)
+            a["fu"], a["fv"], a["uc"], a["vc"] = Ks[:, 0, 0], Ks[:, 1, 1], Ks[:, 0, 2], Ks[:, 1, 2]
+        a["scale"] = np.asarray(self.obj_scale, np.float64)
+        a["ct"] = np.asarray(self.obj_ct, np.float64)
         return dets
 
     def est_pose_batch(self, frames, bboxes, frame_ids=None, camKs=None, frames_dev=None):

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from pix2pose_b200 import _lib, weights as W
-from pix2pose_b200.recognition import _get_boxes
+from pix2pose_b200.recognition import _get_boxes, _get_boxes_batch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -52,6 +52,7 @@ def test_get_boxes_matches_oracle():
         v0, u0 = rng.randint(-60, 460), rng.randint(-60, 620)
         bb = [v0, u0, v0 + rng.randint(1, 300), u0 + rng.randint(1, 300)]
         assert tuple(_get_boxes(1.5, bb, 480, 640)) == tuple(get_boxes(1.5, bb, 480, 640))
+        assert tuple(_get_boxes_batch(1.5, [bb], 480, 640)[0]) == tuple(get_boxes(1.5, bb, 480, 640))
         fb = np.array(bb) * 1.37
         ct = np.array([rng.randint(0, 480), rng.randint(0, 640)])
         assert tuple(_get_boxes(1.5, fb, 480, 640, ct=ct, max_w=128)) == tuple(get_boxes(1.5, fb, 480, 640, ct=ct, max_w=128))
