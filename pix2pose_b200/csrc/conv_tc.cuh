@@ -33,9 +33,10 @@ struct ConvParams {
     int N, H, W;
     int tw, th, nb;
     int tiles_x, tiles_y;
+    int grid_m, grid_n, grid_z;  // tile grid (persistent kernel: tiles are enumerated m fastest, then n, then z)
     // K loop: k-iterations [kstart[z], kstart[z+1]) for phase z = blockIdx.z
     int kstart[5];
-    const int4* kit;  // {map index, dy, dx, c0} per k-iteration
+    const int4* kit;  // {map index | (k16 steps << 8), dy, dx, c0} per k-iteration
     // output tensor (NHWC, hi plane then lo plane `out_plane` elements later)
     __half* out_hi;
     long long out_plane;  // 0 => no lo plane (NP == 1 networks)
@@ -53,6 +54,10 @@ struct ConvParams {
     const int* n_active;  // optional device-side count of live images (tiles past it exit)
     // split-K (Dense layers with a tiny M x N grid): blockIdx.z = K slice of `splitk_chunk` k-iterations; the raw
     // fp32 accumulators go to out_partial[z][row][Cout_pad] and splitk_reduce_kernel finishes the layer.
+    // Phase-fused transposed conv with a regular epilogue: accumulator column c = phase * fused_cout + channel,
+    // phase (a,b) -> output pixel (2y+a, 2x+b).  0 = off.
+    int fused_cout;
+    int halo_ksize;  // halo kernel (conv_tc_halo.cuh): kernel size; p.kit then holds the slab table, kstart[1] = #slabs
     int splitk_chunk;
     float* out_partial;
     long long partial_stride;  // elements between K slices
@@ -149,7 +154,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                 uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
                 uint8_t* sB = sA + Cfg::A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                const CUtensorMap* mA = k.x == 0 ? &mA0 : (k.x == 1 ? &mA1 : (k.x == 2 ? &mA2 : &mA3));
+                const int mi = k.x & 0xff;
+                const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
                 tma_load_5d(mA, &full_bar[s], sA, k.w, x0 + k.z, y0 + k.y, n0, 0);
                 tma_load_4d(&mB, &full_bar[s], sB, 0, nt0, 0, kbeg + it);
             }
@@ -158,26 +164,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(128, BN < 16 ? 16 : BN);
+            int g = 0;  // k16 steps issued so far
             for (int it = 0; it < nk; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
+                const int ksteps = __ldg(&p.kit[kbeg + it].x) >> 8;  // 64-channel chunk: 4; a 32-channel skip slice: 2
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t aA = smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint32_t aB = aA + Cfg::A_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll 1
+                for (int kk = 0; kk < ksteps; ++kk, ++g) {
                     const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
                     const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
                     if (NP == 2) {
-                        const int g = it * 4 + kk;  // k16 step: even -> accumulator 0, odd -> accumulator 1
+                        // k16 step parity: even -> accumulator 0, odd -> accumulator 1
                         umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
                         const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
                         const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
                         umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
                         umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_hi, b_lo, idesc, 1u);
                     } else {
-                        umma_f16(tmem_base, a_hi, b_hi, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
@@ -254,8 +262,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                                                  __uint_as_float(v[4 * g + 3]));
                     }
                 } else if (valid && c0 < p.Cout) {
-                    __half* o_hi = p.out_hi + pix * p.Ctot + p.c_off + c0;
-                    const __half* r_hi = p.res_hi ? p.res_hi + pix * p.res_Ctot + c0 : nullptr;
+                    long long opix = pix;
+                    int cch = c0;
+                    if (p.fused_cout) {
+                        const int phs = c0 / p.fused_cout;
+                        cch = c0 - phs * p.fused_cout;
+                        opix = (static_cast<long long>(n) * p.OH + (2 * y + (phs >> 1))) * p.OW + (2 * x + (phs & 1));
+                    }
+                    __half* o_hi = p.out_hi + opix * p.Ctot + p.c_off + cch;
+                    const __half* r_hi = p.res_hi ? p.res_hi + opix * p.res_Ctot + cch : nullptr;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {  // 8 channels per 16-byte store
                         uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);

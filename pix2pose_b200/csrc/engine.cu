@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <mutex>
 
+#include "conv_tc_halo.cuh"
 #include "net_kernels.cuh"
 
 namespace p2p {
@@ -172,7 +173,7 @@ struct PlanBuilder {
         conv("convT2", K_CONVT, 5, {all(d1u)}, {{"convT2", "bn_convT2"}}, d2, ACT_LRELU);
         conv("deconv2", K_CONV, 5, {all(d2), s2}, {{"deconv2", "bn_deconv2"}}, d2u, ACT_LRELU);
         const int d3 = T("d3", 64, 64, 64), d3u = T("d3_uni", 64, 64, 128);
-        conv("convT3", K_CONVT, 5, {all(d2u)}, {{"convT3", "bn_convT3"}}, d3, ACT_LRELU);
+        conv("convT3", K_CONVT_FUSED, 5, {all(d2u)}, {{"convT3", "bn_convT3"}}, d3, ACT_LRELU);  // Cout 64: N = 4 x 64 fills the tile
         conv("deconv3", K_CONV, 5, {all(d3), s1}, {{"deconv3", "bn_deconv3"}}, d3u, ACT_LRELU);
         conv("heads", K_CONVT_FUSED, 5, {all(d3u)}, {{"convT_xyz", ""}, {"convT_prob", ""}}, -1, ACT_HEADS);
     }
@@ -288,7 +289,26 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         }
         c.kstart[1] = static_cast<int>(c.kit.size());
     }
-    if (c.kind == K_CONVT_FUSED) { c.BN = 16; c.Cout_pad = 16; }
+    c.halo = false;
+    c.slabs.clear();
+    if (c.kind == K_CONV && c.ksize >= 3 && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() <= 2 && c.Cout >= 64) {
+        c.halo = true;
+        int src_base = 0;
+        for (size_t si = 0; si < c.srcs.size(); ++si) {
+            const SrcSpec& sp = c.srcs[si];
+            const int nch = chunks(sp.c_count);
+            for (int ch = 0; ch < nch; ++ch) {
+                const int nvalid = std::min(64, sp.c_count - ch * 64);
+                c.slabs.push_back(make_int4(static_cast<int>(si) | (((nvalid + 15) / 16) << 8), sp.c_begin + ch * 64, src_base + ch, nch));
+            }
+            src_base += c.ksize * c.ksize * nch;
+        }
+    }
+    if (c.kind == K_CONVT_FUSED) {
+        if (c.act == ACT_HEADS) { c.BN = 16; c.Cout_pad = 16; }
+        else { c.BN = 128; c.Cout_pad = (c.Cout + 127) / 128 * 128; }
+    }
+    for (size_t i = 0; i < c.kit.size(); ++i) c.kit[i].x |= ((c.kw[i].nvalid + 15) / 16) << 8;  // k16 steps actually needed
     if (c.kind == K_DENSE && c.kit.size() >= 64) {  // dense_1: K = 32768 -> 32 slices of 16 k-iterations
         c.splitk_chunk = 16;
         c.splitk = static_cast<int>((c.kit.size() + c.splitk_chunk - 1) / c.splitk_chunk);
@@ -402,6 +422,8 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaGetDevice(&dev));
     P2P_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
+    if (const char* e = getenv("P2P_HALO")) use_halo = atoi(e) != 0;
 
     tensors.resize(plan.tensors.size());
     for (size_t i = 0; i < plan.tensors.size(); ++i) {
@@ -451,6 +473,21 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
             encode(&rt.mapA[mi], base, 5, dims, str, box);
         }
         for (size_t mi = c.maps.size(); mi < 4; ++mi) rt.mapA[mi] = rt.mapA[0];
+        memset(rt.mapHalo, 0, sizeof(rt.mapHalo));
+        if (c.halo) {
+            rt.slabs.upload(c.slabs.data(), c.slabs.size());
+            const int pad = (c.ksize - 1) / 2;
+            for (size_t si = 0; si < c.srcs.size(); ++si) {
+                const SrcSpec& sp = c.srcs[si];
+                const TensorSpec& t = plan.tensors[sp.tensor];
+                const cuuint64_t C = t.C, W = t.W, H = t.H;
+                cuuint64_t dims[5] = {(cuuint64_t)(sp.c_begin + sp.c_count), W, H, (cuuint64_t)cap, (cuuint64_t)np};
+                cuuint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, static_cast<cuuint64_t>(cap) * H * W * C * 2};
+                cuuint32_t box[5] = {64, 16, (cuuint32_t)(16 + 2 * pad), 1, (cuuint32_t)np};
+                encode(&rt.mapHalo[si], tensors[sp.tensor].buf.p, 5, dims, str, box);
+            }
+            if (c.srcs.size() < 2) rt.mapHalo[1] = rt.mapHalo[0];
+        }
     }
     P2P_CUDA(cudaDeviceSynchronize());
 }
@@ -563,7 +600,16 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
             for (int ph = 0; ph < 4; ++ph) {
                 int cb = 0;
                 for (auto& q : pw) {
-                    for (int co = 0; co < q.cout; ++co) { sc[ph * tot + cb + co] = 1.f / wscale; sh[ph * tot + cb + co] = q.b[co]; }
+                    for (int co = 0; co < q.cout; ++co) {
+                        float s1 = 1.f, t1 = q.b[co];
+                        if (q.bn) {
+                            const float g = q.bn[co], be = q.bn[q.cout + co], mu = q.bn[2 * q.cout + co], var = q.bn[3 * q.cout + co];
+                            s1 = g / sqrtf(var + 1e-3f);
+                            t1 = be - mu * s1 + q.b[co] * s1;
+                        }
+                        sc[ph * tot + cb + co] = s1 / wscale;
+                        sh[ph * tot + cb + co] = t1;
+                    }
                     cb += q.cout;
                 }
             }
@@ -598,6 +644,30 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
 namespace {
 
 template <int BN, int NP>
+void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const ConvParams& p, int ctas, cudaStream_t s) {
+    using Cfg = ConvCfg<BN, NP>;
+    static bool configured = false;
+    if (!configured) {
+        P2P_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    conv_tc_persistent_kernel<BN, NP><<<ctas, 192, Cfg::SMEM_BYTES, s>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
+    P2P_CUDA(cudaGetLastError());
+}
+
+template <int BN, int NP>
+void launch_conv_halo(const CUtensorMap* mH, const CUtensorMap& mB, const ConvParams& p, int ctas, cudaStream_t s) {
+    using HC = HaloCfg<BN, NP>;
+    static bool configured = false;
+    if (!configured) {
+        P2P_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, HC::SMEM_BYTES));
+        configured = true;
+    }
+    conv_tc_halo_kernel<BN, NP><<<ctas, 192, HC::SMEM_BYTES, s>>>(mH[0], mH[1], mB, p);
+    P2P_CUDA(cudaGetLastError());
+}
+
+template <int BN, int NP>
 void launch_conv(const CUtensorMap* mA, const CUtensorMap& mB, const ConvParams& p, dim3 grid, cudaStream_t s) {
     using Cfg = ConvCfg<BN, NP>;
     static bool configured = false;
@@ -629,7 +699,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
     for (const Step& st : plan.steps) {
         if (st.kind == S_IM2COL) {
             const long long total = static_cast<long long>(n) * 64 * 64 * (st.d / 8);
-            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, num_sms * 16));
+            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 22));
             im2col_stem_kernel<<<blocks, 256, 0, s>>>(x_dev, tensors[st.a].buf.p, tensors[st.a].plane, n, st.b, st.c, st.d, n_active);
             P2P_CUDA(cudaGetLastError());
             ++launches;
@@ -637,7 +707,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
         } else if (st.kind == S_MAXPOOL) {
             const TensorSpec& ti = plan.tensors[st.a];
             const long long total = static_cast<long long>(n) * (ti.H / 2) * (ti.W / 2) * (ti.C / 8);
-            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, num_sms * 16));
+            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 22));
             maxpool3x3s2_kernel<<<blocks, 256, 0, s>>>(tensors[st.a].buf.p, tensors[st.a].plane, tensors[st.b].buf.p,
                                                        tensors[st.b].plane, n, ti.H, ti.W, ti.C, n_active);
             P2P_CUDA(cudaGetLastError());
@@ -672,6 +742,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             }
             p.n_active = n_active;
             p.Cout_pad = c.Cout_pad;
+            if (c.kind == K_CONVT_FUSED && c.act != ACT_HEADS) p.fused_cout = c.Cout / 4;
             if (c.splitk > 1) {
                 p.splitk_chunk = c.splitk_chunk;
                 p.out_partial = partial.p;
@@ -679,7 +750,35 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             }
             const int tiles_n = (n + c.nb - 1) / c.nb;
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
-            if (np == 2) {
+            p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
+            if (use_halo && c.halo && (c.BN == 128 || c.BN == 64)) {
+                p.tw = 8; p.th = 16; p.nb = 1;
+                p.tiles_x = c.W / 8; p.tiles_y = c.H / 16;
+                p.grid_m = p.tiles_x * p.tiles_y * n; p.grid_z = 1;
+                p.halo_ksize = c.ksize;
+                p.kit = rt.slabs.p;
+                p.kstart[0] = 0;
+                for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
+                const int ctas = std::min<long long>(static_cast<long long>(p.grid_m) * p.grid_n, num_sms);
+                if (np == 2) {
+                    if (c.BN == 128) launch_conv_halo<128, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    else launch_conv_halo<64, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
+                } else {
+                    if (c.BN == 128) launch_conv_halo<128, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    else launch_conv_halo<64, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
+                }
+            } else if (persistent) {
+                const int ctas = std::min<long long>(static_cast<long long>(grid.x) * grid.y * grid.z, num_sms);
+                if (np == 2) {
+                    if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, p, ctas, s);
+                    else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, p, ctas, s);
+                } else {
+                    if (c.BN == 128) launch_conv_persistent<128, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                    else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                }
+            } else if (np == 2) {
                 if (c.BN == 128) launch_conv<128, 2>(rt.mapA, mc.mapB, p, grid, s);
                 else if (c.BN == 64) launch_conv<64, 2>(rt.mapA, mc.mapB, p, grid, s);
                 else launch_conv<16, 2>(rt.mapA, mc.mapB, p, grid, s);

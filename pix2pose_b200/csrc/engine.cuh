@@ -46,6 +46,8 @@ struct ConvSpec {
     int Cin = 0, Cout = 0, Cout_pad = 0, BN = 0;
     int kstart[5] = {0, 0, 0, 0, 0};
     int splitk = 1, splitk_chunk = 0;  // K slices (Dense layers whose M x N grid cannot fill the GPU)
+    bool halo = false;                 // eligible for conv_tc_halo_kernel (k x k stride-1 conv, W % 8 == 0, H % 16 == 0)
+    std::vector<int4> slabs;           // halo kernel: one entry per (source, 64-channel chunk)
     int oy_off[4] = {0, 0, 0, 0}, ox_off[4] = {0, 0, 0, 0}, sy = 1, sx = 1;
     std::vector<int4> kit;
     std::vector<KWeight> kw;
@@ -94,9 +96,11 @@ class Engine {
     std::vector<Tensor> tensors;
     DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
     DevBuf<float> partial;       // split-K scratch [slices][cap][Cout_pad]
-    struct ConvRt { DevBuf<int4> kit; CUtensorMap mapA[4]; };
+    struct ConvRt { DevBuf<int4> kit, slabs; CUtensorMap mapA[4]; CUtensorMap mapHalo[2]; };
     std::vector<ConvRt> conv_rt;
     int num_sms = 148;
+    bool use_halo = false;    // conv_tc_halo_kernel for eligible convs (P2P_HALO=1)
+    bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
 
     // x_dev -> dec_dev / prob_dev for n <= cap crops; n_active (device int) optionally limits work further.
     void forward(const Model& m, const float* x_dev, int n, float* dec_dev, float* prob_dev, const int* n_active,

@@ -37,19 +37,19 @@ template <int N>
 P2P_HD inline void jacobi_eig_sym(double* A, double* Vt, double* w) {
     for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) Vt[i * N + j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < N; ++i) {
-            diag += A[i * N + i] * A[i * N + i];
-            for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
-        }
-        if (off <= 1e-30 * diag || off == 0.0) break;
+    // Rotations whose off-diagonal element is below eps * ||A||_F are skipped; a sweep without any
+    // rotation ends the iteration (rank-deficient 5-point systems would otherwise spin on noise).
+    double fro = 0.0;
+    for (int i = 0; i < N * N; ++i) fro += A[i] * A[i];
+    const double tiny = 1e-17 * sqrt(fro);
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool rotated = false;
         for (int p = 0; p < N - 1; ++p)
             for (int q = p + 1; q < N; ++q) {
                 const double apq = A[p * N + q];
-                if (apq == 0.0) continue;
+                if (fabs(apq) <= tiny) continue;
+                rotated = true;
                 const double app = A[p * N + p], aqq = A[q * N + q];
-                if (fabs(apq) <= 1e-18 * sqrt(fabs(app * aqq)) && fabs(apq) < 1e-300) continue;
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
@@ -69,6 +69,7 @@ P2P_HD inline void jacobi_eig_sym(double* A, double* Vt, double* w) {
                     Vt[q * N + k] = s * vpk + c * vqk;
                 }
             }
+        if (!rotated) break;
     }
     for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
     for (int i = 0; i < N - 1; ++i) {  // selection sort, descending
