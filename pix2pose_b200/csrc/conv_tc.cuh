@@ -75,7 +75,10 @@ struct ConvCfg {
     // for the 2^-11-times-smaller cross terms.  The tensor core rounds the fp32 accumulator toward zero
     // after every MMA; splitting the chains divides that bias (measured: resnet50 decode max error
     // 1.0e-3 with one accumulator).  The epilogue adds the three.
-    static constexpr int NACC = NP == 2 ? 3 : 1;
+    // BN = 256 (N = 256 MMAs halve the shared-memory operand reads per FLOP -- the kernel is smem-bandwidth-bound at
+    // N = 128: 8 KB of operands per 64-cycle MMA = the full 128 B/cycle, before TMA writes) only has room for two:
+    // all hi*hi products in one chain, cross terms in the other.
+    static constexpr int NACC = NP == 2 ? (BN == 256 ? 2 : 3) : 1;
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;  // TMEM columns between accumulators
     static constexpr uint32_t TMEM_COLS = NACC * ACC_STRIDE <= 32 ? 32 : (NACC * ACC_STRIDE <= 64 ? 64 : (NACC * ACC_STRIDE <= 128 ? 128 : (NACC * ACC_STRIDE <= 256 ? 256 : 512)));
 };

@@ -50,9 +50,13 @@ template <int BN, int NP>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_empty_bar,
                                               const TileCoord& tc, int hl, int wl, int nl, int n_limit) {
     using Cfg = ConvCfg<BN, NP>;
-    constexpr int NCOL = BN < 32 ? 16 : BN;
+    constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns drained per pass
+    constexpr int NPASS = BN > 128 ? BN / 128 : 1;
     const bool splitk = p.splitk_chunk > 0;
     const int z = tc.z, zi = splitk ? 0 : z;
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+    const uint32_t tcol = taddr + pass * NCOL;
     __syncwarp();  // lanes may arrive here diverged (per-lane store paths of the previous tile); tcgen05.ld is .aligned
     do {
             // ---- drain TMEM into registers, summing the fp16x3 accumulators
@@ -75,25 +79,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
                 for (int ch = 0; ch < NCOL / 32; ++ch) {
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr + ch * 32, v);
+                    tmem_ld_32x32(tcol + ch * 32, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[ch * 32 + j] = __uint_as_float(v[j]);
-                    if (Cfg::NACC == 3) {
-                        tmem_ld_32x32(taddr + Cfg::ACC_STRIDE + ch * 32, v);
+                    if (Cfg::NACC >= 2) {
+                        tmem_ld_32x32(tcol + Cfg::ACC_STRIDE + ch * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[ch * 32 + j] += __uint_as_float(v[j]);
-                        tmem_ld_32x32(taddr + 2 * Cfg::ACC_STRIDE + ch * 32, v);
+                    }
+                    if (Cfg::NACC == 3) {
+                        tmem_ld_32x32(tcol + 2 * Cfg::ACC_STRIDE + ch * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[ch * 32 + j] += __uint_as_float(v[j]);
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);  // TMEM is free: the next tile's MMAs may start
+            if (pass == NPASS - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar);  // TMEM is free: the next tile's MMAs may start
+            }
 
             // ---- BN / bias / residual / activation / hi-lo split / stores, from registers
             const int y = tc.y0 + hl, x = tc.x0 + wl, n = tc.n0 + nl;
@@ -119,7 +127,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             if (BN >= 32) {
 #pragma unroll
                 for (int ch = 0; ch < NCOL / 32; ++ch) {
-                    const int c0 = tc.nt0 + ch * 32;
+                    const int c0 = tc.nt0 + pass * NCOL + ch * 32;
                     if (splitk) {
                         float4* dst = reinterpret_cast<float4*>(p.out_partial + z * p.partial_stride + pix * p.Cout_pad + c0);
 #pragma unroll
@@ -165,6 +173,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 }
             }
     } while (false);
+    }
 }
 
 template <int BN, int NP>
@@ -256,11 +265,13 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                         const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
                         const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
                         if (NP == 2) {
-                            umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
+                            constexpr uint32_t cross = (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
+                            if (Cfg::NACC == 3) umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
+                            else umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                             const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
                             const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                            umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
-                            umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_hi, b_lo, idesc, 1u);
+                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
+                            umma_f16(tmem_base + cross, a_hi, b_lo, idesc, 1u);
                         } else {
                             umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                         }

@@ -194,6 +194,7 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
     c.Cout = 0;
     for (auto& w : c.parts) c.Cout += layer_cout(L[find_layer(L, w.layer)]);
     if (c.Cout < 64) { c.BN = 16; c.Cout_pad = 16; }
+    else if (c.Cout % 256 == 0 && getenv("P2P_BN256") && atoi(getenv("P2P_BN256"))) { c.BN = 256; c.Cout_pad = c.Cout; }
     else if (c.Cout % 128 == 0) { c.BN = 128; c.Cout_pad = c.Cout; }
     else { c.BN = 64; c.Cout_pad = (c.Cout + 63) / 64 * 64; }
 
@@ -751,6 +752,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             const int tiles_n = (n + c.nb - 1) / c.nb;
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
+            P2P_CHECK(c.BN != 256 || persistent, "BN = 256 tiles need the persistent kernel");
             if (use_halo && c.halo && (c.BN == 128 || c.BN == 64)) {
                 p.tw = 8; p.th = 16; p.nb = 1;
                 p.tiles_x = c.W / 8; p.tiles_y = c.H / 16;
@@ -769,7 +771,10 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 }
             } else if (persistent) {
                 const int ctas = std::min<long long>(static_cast<long long>(grid.x) * grid.y * grid.z, num_sms);
-                if (np == 2) {
+                if (c.BN == 256) {
+                    if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, p, ctas, s);
+                    else launch_conv_persistent<256, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                } else if (np == 2) {
                     if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, p, ctas, s);
                     else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, p, ctas, s);
                     else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, p, ctas, s);

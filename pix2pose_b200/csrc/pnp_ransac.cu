@@ -30,6 +30,24 @@ __device__ __forceinline__ float reproj_err_f32(const double* R, const double* t
     return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
 
+// Inlier test for the scoring kernel: the same decision as reproj_err_f32(...) <= thr2, but evaluated in fp32 first;
+// only correspondences whose fp32 error lands within `margin` of the threshold (fp32 error bound ~1e-3 px^2 at
+// 5 px) or is not finite are re-evaluated through the exact fp64 path.  Rf/tf are float copies of R/t.
+__device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t, const float* Rf, const float* tf, const float* o,
+                                               const float* ip, const PnpProblem& pr, float fuf, float fvf, float ucf, float vcf,
+                                               float thr2) {
+    const float X = o[0], Y = o[1], Z = o[2];
+    const float x = fmaf(Rf[0], X, fmaf(Rf[1], Y, fmaf(Rf[2], Z, tf[0])));
+    const float y = fmaf(Rf[3], X, fmaf(Rf[4], Y, fmaf(Rf[5], Z, tf[1])));
+    const float z = fmaf(Rf[6], X, fmaf(Rf[7], Y, fmaf(Rf[8], Z, tf[2])));
+    const float iz = __frcp_rn(z);
+    const float dx = ip[0] - fmaf(x * iz, fuf, ucf), dy = ip[1] - fmaf(y * iz, fvf, vcf);
+    const float e = fmaf(dx, dx, dy * dy);
+    const float margin = 0.01f * thr2 + 0.05f;
+    if (fabsf(e - thr2) > margin && fabsf(z) > 1e-3f) return e <= thr2;   // NaN/inf fall through to the exact path
+    return reproj_err_f32(R, t, o, ip, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;
+}
+
 // ---- (1) hypotheses: RNG replay by thread 0, then one 5-point EPnP per thread
 __global__ void __launch_bounds__(kHypThreads) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
                                                                  const float* __restrict__ obj, const float* __restrict__ img,
@@ -84,11 +102,14 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
     t[0] = m[9]; t[1] = m[10]; t[2] = m[11];
     const float* o = obj + pr.offset * 3;
     const float* ip = img + pr.offset * 2;
+    float Rf[9], tf[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rf[i] = static_cast<float>(R[i]);
+    tf[0] = static_cast<float>(t[0]); tf[1] = static_cast<float>(t[1]); tf[2] = static_cast<float>(t[2]);
+    const float fuf = static_cast<float>(pr.fu), fvf = static_cast<float>(pr.fv), ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
     int cnt = 0;
-    for (int i = lane; i < pr.n; i += 32) {
-        const float e = reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc);
-        cnt += (e <= thr2) ? 1 : 0;  // NaN compares false, as in findInliers
-    }
+    for (int i = lane; i < pr.n; i += 32)
+        cnt += is_inlier_fast(R, t, Rf, tf, o + 3 * i, ip + 2 * i, pr, fuf, fvf, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     if (lane == 0) counts[blockIdx.y * iters + h] = cnt;
