@@ -476,12 +476,14 @@ void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, 
     cudaStream_t s = engine->stream;
     host_dets_.assign(dets, dets + n);
     long long px = 0;
+    int max_cap = 0;
     for (int d = 0; d < n; ++d) {
         DetIn& di = host_dets_[d];
         P2P_CHECK(di.frame >= 0 && di.frame < F, "detection %d: frame %d outside [0,%d)", d, di.frame, F);
         const long long side = std::max(0, di.box1[1] - di.box1[0]);
         di.cap_px = static_cast<int>(std::min<long long>(side * side, 1 << 30));
         di.pool_off = px;
+        max_cap = std::max(max_cap, di.cap_px);
         px += static_cast<long long>(di.cap_px) * n_th;
     }
     ensure_pool(px + 1);
@@ -530,7 +532,7 @@ void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, 
                                                   xyz_u8_.p, valid_.p, obj_.p, img_.p, problems_.p);
     P2P_CUDA(cudaGetLastError());
     launches += 5;
-    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s);
+    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s, max_cap);
     select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
     P2P_CUDA(cudaGetLastError());
     launches += 1;

@@ -85,34 +85,46 @@ __global__ void __launch_bounds__(kHypThreads) ransac_hyp_kernel(const PnpProble
     }
 }
 
-// ---- (2) scoring: one warp per hypothesis over all correspondences of its problem
+// ---- (2) scoring: one warp per hypothesis over the correspondences.  A block stages a tile of kScoreTile
+// correspondences of its problem in shared memory ONCE and its 8 warps walk all `iters` hypotheses over it
+// (warp w takes hypotheses w, w+8, ...); per-tile inlier counts are warp-shuffle-reduced and added to
+// counts[problem][hypothesis].  (Reading the points straight from global memory made this kernel L1/L2-bandwidth
+// bound: every point was fetched `iters` times.)
+constexpr int kScoreTile = 2048;
+
 __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const PnpProblem* __restrict__ probs,
                                                                        const float* __restrict__ obj,
                                                                        const float* __restrict__ img,
                                                                        const double* __restrict__ hyp, int* __restrict__ counts,
                                                                        int iters, float thr2) {
+    __shared__ float s_o[kScoreTile * 3];
+    __shared__ float s_ip[kScoreTile * 2];
     const PnpProblem pr = probs[blockIdx.y];
-    const int h = blockIdx.x * kScoreWarps + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (pr.n < 6 || h >= iters) return;
-    const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
-    double R[9], t[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = m[i];
-    t[0] = m[9]; t[1] = m[10]; t[2] = m[11];
-    const float* o = obj + pr.offset * 3;
-    const float* ip = img + pr.offset * 2;
-    float Rf[9], tf[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Rf[i] = static_cast<float>(R[i]);
-    tf[0] = static_cast<float>(t[0]); tf[1] = static_cast<float>(t[1]); tf[2] = static_cast<float>(t[2]);
+    const int base = blockIdx.x * kScoreTile;
+    if (pr.n < 6 || base >= pr.n) return;
+    const int cnt_pts = min(kScoreTile, pr.n - base);
+    const float* go = obj + (pr.offset + base) * 3;
+    const float* gi = img + (pr.offset + base) * 2;
+    for (int i = threadIdx.x; i < cnt_pts * 3; i += blockDim.x) s_o[i] = go[i];
+    for (int i = threadIdx.x; i < cnt_pts * 2; i += blockDim.x) s_ip[i] = gi[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float fuf = static_cast<float>(pr.fu), fvf = static_cast<float>(pr.fv), ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
-    int cnt = 0;
-    for (int i = lane; i < pr.n; i += 32)
-        cnt += is_inlier_fast(R, t, Rf, tf, o + 3 * i, ip + 2 * i, pr, fuf, fvf, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
+    for (int h = warp; h < iters; h += kScoreWarps) {
+        const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
+        double R[9], t[3];
+        float Rf[9], tf[3];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if (lane == 0) counts[blockIdx.y * iters + h] = cnt;
+        for (int i = 0; i < 9; ++i) { R[i] = m[i]; Rf[i] = static_cast<float>(R[i]); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { t[i] = m[9 + i]; tf[i] = static_cast<float>(t[i]); }
+        int cnt = 0;
+        for (int i = lane; i < cnt_pts; i += 32)
+            cnt += is_inlier_fast(R, t, Rf, tf, s_o + 3 * i, s_ip + 2 * i, pr, fuf, fvf, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane == 0 && cnt) atomicAdd(&counts[blockIdx.y * iters + h], cnt);
+    }
 }
 
 // ---- (3) replay of RANSACPointSetRegistrator::run's accept / adaptive-termination rule + inlier mask
@@ -388,7 +400,7 @@ void PnpSolver::ensure(int n_problems, int iters) {
 
 void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, const float* obj_dev, const float* img_dev,
                             uint8_t* mask_dev, PnpResult* results_dev, float reproj_err, int iters, double confidence,
-                            cudaStream_t s) {
+                            cudaStream_t s, int max_n) {
     if (n_problems <= 0) return;
     P2P_CHECK(iters >= 1 && iters <= 4096, "iterationsCount %d outside [1,4096]", iters);
     P2P_CHECK(confidence > 0 && confidence < 1, "confidence must be in (0,1)");
@@ -396,7 +408,9 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     const float thr2 = static_cast<float>(static_cast<double>(reproj_err) * static_cast<double>(reproj_err));
     ransac_hyp_kernel<<<n_problems, kHypThreads, iters * 5 * sizeof(int), s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
     P2P_CUDA(cudaGetLastError());
-    dim3 g((iters + kScoreWarps - 1) / kScoreWarps, n_problems);
+    P2P_CHECK(max_n >= 0, "max_n must be the largest correspondence count of the batch");
+    P2P_CUDA(cudaMemsetAsync(counts_.p, 0, sizeof(int) * static_cast<size_t>(n_problems) * iters, s));
+    dim3 g(std::max(1, (max_n + kScoreTile - 1) / kScoreTile), n_problems);
     ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, thr2);
     P2P_CUDA(cudaGetLastError());
     ransac_select_kernel<<<n_problems, 256, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, best_.p, mask_dev,
@@ -422,7 +436,7 @@ void PnpSolver::solve_host(const double* obj, const double* img, int n, const do
     if (h_mask_.n < static_cast<size_t>(n) + 1) h_mask_.alloc(static_cast<size_t>(n) + 1);
     h_prob_.upload(&pr, 1, stream_);
     if (h_res_.n < 1) h_res_.alloc(1);
-    solve_batch(h_prob_.p, 1, h_obj_.p, h_img_.p, h_mask_.p, h_res_.p, reproj_err, iters, confidence, stream_);
+    solve_batch(h_prob_.p, 1, h_obj_.p, h_img_.p, h_mask_.p, h_res_.p, reproj_err, iters, confidence, stream_, n);
     P2P_CUDA(cudaMemcpyAsync(out, h_res_.p, sizeof(PnpResult), cudaMemcpyDeviceToHost, stream_));
     if (mask_out && n > 0) P2P_CUDA(cudaMemcpyAsync(mask_out, h_mask_.p, n, cudaMemcpyDeviceToHost, stream_));
     P2P_CUDA(cudaStreamSynchronize(stream_));

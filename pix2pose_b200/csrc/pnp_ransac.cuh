@@ -41,7 +41,7 @@ class PnpSolver {
     // Device-side batch: pools obj (total x 3 f32), img (total x 2 f32), mask (total u8, written).
     void solve_batch(const PnpProblem* problems_dev, int n_problems, const float* obj_dev, const float* img_dev,
                      uint8_t* mask_dev, PnpResult* results_dev, float reproj_err, int iters, double confidence,
-                     cudaStream_t s);
+                     cudaStream_t s, int max_n);  // max_n >= the largest problem's n (sizes the scoring grid)
     // Host convenience: one problem, double inputs converted to float32 like OpenCV does.
     void solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,
                     double confidence, PnpResult* out, uint8_t* mask_out);

@@ -150,25 +150,28 @@ class pix2pose():
     def get_boxes(self, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
         return _get_boxes(self.box_size, bbox, v_max, u_max, ct, max_w)
 
+    # The device pipeline (stage buffers, candidate pools, PnP scratch) does not depend on the object: all
+    # pix2pose instances that share an engine and a threshold count share ONE pipeline, like the reference's
+    # per-object models share one TF session (tools/5_evaluation_bop_basic.py:112-114).
+    _shared_pipes = {}
+
     def _pipeline(self, n):
-        key = (len(self.th_o), max(self._max_dets, n))
-        if self._pipe is None or self._pipe_key[0] != key[0] or self._pipe_key[1] < n:
-            self._release_pipe()
+        eng = self.generator_train.engine
+        key = (id(eng), len(self.th_o))
+        ent = pix2pose._shared_pipes.get(key)
+        want = max(self._max_dets, n)
+        if ent is None or ent[1] < n:
             h = ctypes.c_void_p()
-            _lib.check(_lib.lib().p2p_pipeline_create(self.generator_train.engine.handle, key[1], key[0], ctypes.byref(h)))
-            self._pipe, self._pipe_key = h, key
+            _lib.check(_lib.lib().p2p_pipeline_create(eng.handle, want, len(self.th_o), ctypes.byref(h)))
+            if ent is not None:
+                _lib.lib().p2p_pipeline_destroy(ent[0])
+            ent = (h, want, eng)          # keeps the engine alive as long as the pipeline
+            pix2pose._shared_pipes[key] = ent
+        self._pipe = ent[0]
         return self._pipe
 
     def _release_pipe(self):
-        if getattr(self, "_pipe", None) is not None:
-            _lib.lib().p2p_pipeline_destroy(self._pipe)
-            self._pipe = None
-
-    def __del__(self):
-        try:
-            self._release_pipe()
-        except Exception:
-            pass
+        self._pipe = None
 
     @property
     def launch_count(self):

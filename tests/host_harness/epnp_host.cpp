@@ -35,7 +35,7 @@ void host_rodrigues_roundtrip(const double* R9, double* r3, double* R9out) {
 void host_eig12(const double* A, double* Vt, double* w) {
     double B[144];
     for (int i = 0; i < 144; ++i) B[i] = A[i];
-    epnp::jacobi_eig_sym<12>(B, Vt, w);
+    epnp::tridiag_eig_sym<12>(B, Vt, w);
 }
 }
 

@@ -90,8 +90,8 @@ def test_ransac_emulation_matches_cv2_solvepnpransac(host_harness):
         total += 1
         same = np.array_equal(np.nonzero(mask)[0], inl[:, 0])
         exact += same
-        if same:
-            assert np.abs(rvec - rvc[:, 0]).max() < 1e-6 and np.abs(tvec - tvc[:, 0]).max() < 1e-4
+        if same:   # same consensus set -> same refit (up to the null-space noise of very small sets)
+            assert np.abs(rvec - rvc[:, 0]).max() < 1e-5 and np.linalg.norm(tvec - tvc[:, 0]) / np.linalg.norm(tvc) < 1e-5
         elif n >= 100:
             assert abs(int(mask.sum()) - len(inl)) <= 0.05 * n and np.abs(rvec - rvc[:, 0]).max() < 2e-2
     assert exact >= 0.6 * total, (exact, total)

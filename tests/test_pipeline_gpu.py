@@ -120,3 +120,25 @@ def test_batch_equals_singles_at_config3_size(rec):
         assert one.n_inliers[0] == res.n_inliers[i]
     rec16 = res.records()
     assert rec16.shape == (256, 16) and np.array_equal(rec16[:, 15], np.arange(256))
+
+
+def test_multi_object_stream_matches_per_object_calls(frame):
+    """SURVEY §8d config 4 in miniature: two objects (two weight sets, one engine + pipeline), interleaved
+    detection stream; every detection gets exactly the pose its own object's recogniser computes alone."""
+    from pix2pose_b200.stream import MultiObjectRecognizer
+    objs = {3: np.array([50., 40., 60., 0., 0., 0.]), 7: np.array([30., 30., 80., 1., -2., 3.])}
+    wts = {3: W.synthetic_weights("paper", 1), 7: W.synthetic_weights("paper", 2)}
+    multi = MultiObjectRecognizer(wts, K_LM, 640, 480, objs, backbone="paper", capacity=16, max_dets=16)
+    rng = np.random.RandomState(3)
+    frames = np.stack([frame, frame[::-1].copy()])
+    rois, oids, fids = [], [], []
+    for i in range(10):
+        cy, cx, h, w = rng.randint(80, 400), rng.randint(80, 560), rng.randint(50, 120), rng.randint(50, 120)
+        rois.append([cy - h // 2, cx - w // 2, cy + h // 2, cx + w // 2]); oids.append(3 if i % 2 == 0 else 7); fids.append(i % 2)
+    rec, status = multi.est_pose_stream(frames, rois, oids, fids)
+    assert rec.shape == (10, 16) and np.array_equal(rec[:, 15], np.arange(10))
+    for i in range(10):
+        one = multi.models[oids[i]].est_pose_batch(frames[fids[i]], [rois[i]])
+        assert one.status[0] == status[i]
+        assert np.array_equal(one.R[0].ravel(), rec[i, :9]) and np.array_equal(one.t[0], rec[i, 9:12])
+    assert len({tuple(rec[0, :9]), tuple(rec[1, :9])}) == 2
