@@ -1,43 +1,31 @@
-// Halo-reuse variant of the implicit-GEMM convolution for k x k stride-1 'same' convs (k = 3, 5):
+// Slab-reuse variant of the implicit-GEMM convolution for k x k stride-1 'same' convs (k = 3, 5):
 // deconv1/2/3 of the decoder (66 % of the network's FLOPs, ae_model.py:209, 218, 228) and the 3x3
 // convs of the ResNet bottlenecks (resnet50_mod.py:62-65).
 //
-// The generic kernel re-fetches the 128-pixel A tile for every tap (25 shifted copies for 5x5): all L2
-// hits, but 32 KB per 768 MMA cycles on top of the weights makes the kernel TMA-supply-bound
-// (profiles/r01_summary.md: 66 % tensor-pipe active).  Here one TMA box per 64-channel slab brings the
-// input tile WITH its halo -- 16 x (16 + 2*pad) pixels x 64 ch x {hi,lo} = 80 KB -- into shared memory once,
-// and every tap's A operand is a UMMA descriptor pointing into that slab:
-//   output tile = 8 (w) x 16 (h) pixels; MMA row r = h*8 + w; the 8 rows of a core-matrix group are the 8
-//   consecutive pixels of one halo row (128 B apart), groups are one halo row (16 px = 2048 B) apart (SBO);
-//   tap (dy,dx) starts at halo pixel dy*16 + dx, i.e. 128-B-aligned but not 1024-B-aligned, so the descriptor
-//   carries base_offset = (addr >> 7) & 7 for the 128-byte swizzle phase.
-// Only the weights stream per tap (4 stages x 32 KB).  A traffic drops ~10x (5x5) / ~4x (3x3).
+// Why: the generic kernel is shared-memory-bandwidth bound (profiles/r01_summary.md).  Each 128x128x16 MMA
+// reads 8 KB of operands from smem in 64 cycles -- the full 128 B/cycle -- and the TMA writes that feed it
+// (A 32 KB + B 32 KB per 12 MMAs = 5.3 KB per MMA) compete for the same port: 13.3 KB / 128 B/clk = 104 cycles
+// per MMA, i.e. the measured 66 % tensor-pipe utilisation.  This kernel removes most of the A writes: the output
+// tile is 8 (w) x 16 (h) pixels, and for each 64-channel chunk and each horizontal tap offset dx ONE slab of
+// 8 x (16 + 2*pad) pixels is loaded; the k vertical taps dy are then plain descriptor offsets into it
+// (MMA row r = h*8 + w  <->  slab pixel dy*8 + r: contiguous 128-byte rows, start 1024-B aligned for every dy,
+// so the ordinary K-major SWIZZLE_128B descriptor applies).  A traffic drops by k (5x for 5x5), weights stream
+// per tap as before.
 #pragma once
 #include "conv_tc_persistent.cuh"
 
 namespace p2p {
 
-// smem descriptor for a K-major 128B-swizzled operand whose 8-row groups are `sbo` bytes apart and whose
-// start address is only 128-B aligned (base_offset carries the swizzle phase of the first row).
-__device__ __forceinline__ uint64_t umma_desc_sw128_halo(uint32_t smem_addr, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>(sbo >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;  // base offset
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-
 template <int BN, int NP>
 struct HaloCfg {
-    static constexpr int HALO_W = 16;
-    static constexpr int MAX_ROWS = 20;                                // 16 + 2*2
-    static constexpr int PLANE_BYTES = HALO_W * MAX_ROWS * 128;        // 40 KB per plane
-    static constexpr int HALO_BYTES = NP * PLANE_BYTES;
+    static constexpr int SLAB_W = 8;
+    static constexpr int MAX_ROWS = 20;                               // 16 + 2*2
+    static constexpr int SLAB_BYTES = NP * SLAB_W * MAX_ROWS * 128;   // 40 KB (fp16x3)
+    static constexpr int SLAB_BUFS = 2;
     static constexpr int B_BYTES = NP * BN * 128;
-    static constexpr int B_STAGES = (212 * 1024 - HALO_BYTES) / B_BYTES > 8 ? 8 : (212 * 1024 - HALO_BYTES) / B_BYTES;
-    static constexpr int SMEM_BYTES = HALO_BYTES + B_STAGES * B_BYTES + 1024 + 256;
+    static constexpr int B_ROOM = 208 * 1024 - SLAB_BUFS * SLAB_BYTES;
+    static constexpr int B_STAGES = B_ROOM / B_BYTES > 8 ? 8 : B_ROOM / B_BYTES;
+    static constexpr int SMEM_BYTES = SLAB_BUFS * SLAB_BYTES + B_STAGES * B_BYTES + 1024 + 256;
 };
 
 // slab table entry (p.kit): {map index | (k16 steps << 8), c0, first packed-weight k-iteration of (source, tap 0, chunk), chunks of the source}
@@ -57,21 +45,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
         n_limit = na < n_limit ? na : n_limit;
     }
     const int total = p.grid_m * p.grid_n;
-    const int ks = p.halo_ksize, pad = (ks - 1) / 2, ntaps = ks * ks;
+    const int ks = p.halo_ksize, pad = (ks - 1) / 2;
     const int n_slabs = p.kstart[1];
-    const uint32_t halo_tx = static_cast<uint32_t>(NP) * HC::HALO_W * (16 + 2 * pad) * 128;  // bytes one slab load delivers
-    const uint32_t plane_off = HC::HALO_W * (16 + 2 * pad) * 128;                             // lo plane follows the hi box
+    const int rows = 16 + 2 * pad;
+    const uint32_t slab_tx = static_cast<uint32_t>(NP) * HC::SLAB_W * rows * 128;  // bytes one slab load delivers
+    const uint32_t plane_off = HC::SLAB_W * rows * 128;                             // lo plane follows the hi box
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* sHalo = smem;
-    uint8_t* sB = smem + HC::HALO_BYTES;
+    uint8_t* sSlab = smem;
+    uint8_t* sB = smem + HC::SLAB_BUFS * HC::SLAB_BYTES;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(sB + BS * HC::B_BYTES);
     uint64_t* b_empty = b_full + BS;
-    uint64_t* halo_full = b_empty + BS;
-    uint64_t* halo_empty = halo_full + 1;
-    uint64_t* tmem_full_bar = halo_empty + 1;
+    uint64_t* slab_full = b_empty + BS;
+    uint64_t* slab_empty = slab_full + HC::SLAB_BUFS;
+    uint64_t* tmem_full_bar = slab_empty + HC::SLAB_BUFS;
     uint64_t* tmem_empty_bar = tmem_full_bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
 
@@ -82,8 +71,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(halo_full, 1);
-        mbar_init(halo_empty, 1);
+        for (int s = 0; s < HC::SLAB_BUFS; ++s) {
+            mbar_init(&slab_full[s], 1);
+            mbar_init(&slab_empty[s], 1);
+        }
         mbar_init(tmem_full_bar, 1);
         mbar_init(tmem_empty_bar, 4);
         fence_mbar_init();
@@ -98,21 +89,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int bg = 0, hg = 0;  // weight-stage and halo use counters
+            int bg = 0, sg = 0;  // weight-stage and slab use counters
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, t, n_limit);
                 if (!tc.live) continue;
-                for (int sl = 0; sl < n_slabs; ++sl, ++hg) {
+                for (int sl = 0; sl < n_slabs; ++sl) {
                     const int4 k = __ldg(&p.kit[sl]);
-                    mbar_wait(halo_empty, (hg & 1) ^ 1);
-                    mbar_arrive_expect_tx(halo_full, halo_tx);
                     const CUtensorMap* mA = (k.x & 0xff) == 0 ? &mA0 : &mA1;
-                    tma_load_5d(mA, halo_full, sHalo, k.y, tc.x0 - pad, tc.y0 - pad, tc.n0, 0);
-                    for (int tap = 0; tap < ntaps; ++tap, ++bg) {
-                        const int s = bg % BS;
-                        mbar_wait(&b_empty[s], ((bg / BS) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[s], HC::B_BYTES);
-                        tma_load_4d(&mB, &b_full[s], sB + s * HC::B_BYTES, 0, tc.nt0, 0, k.z + tap * k.w);
+                    for (int dx = 0; dx < ks; ++dx, ++sg) {
+                        const int sb = sg % HC::SLAB_BUFS;
+                        mbar_wait(&slab_empty[sb], ((sg / HC::SLAB_BUFS) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&slab_full[sb], slab_tx);
+                        tma_load_5d(mA, &slab_full[sb], sSlab + sb * HC::SLAB_BYTES, k.y, tc.x0 - pad + dx, tc.y0 - pad, tc.n0, 0);
+                        for (int dy = 0; dy < ks; ++dy, ++bg) {
+                            const int s = bg % BS;
+                            mbar_wait(&b_empty[s], ((bg / BS) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&b_full[s], HC::B_BYTES);
+                            tma_load_4d(&mB, &b_full[s], sB + s * HC::B_BYTES, 0, tc.nt0, 0, k.z + (dy * ks + dx) * k.w);
+                        }
                     }
                 }
             }
@@ -121,42 +115,46 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-            const uint32_t aHalo = smem_u32(sHalo);
-            int bg = 0, hg = 0, tile_i = 0;
+            constexpr uint32_t cross = (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
+            int bg = 0, sg = 0, tile_i = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, t, n_limit);
                 if (!tc.live) continue;
                 mbar_wait(tmem_empty_bar, (tile_i & 1) ^ 1);
                 tc_fence_after();
                 int g = 0;
-                for (int sl = 0; sl < n_slabs; ++sl, ++hg) {
+                for (int sl = 0; sl < n_slabs; ++sl) {
                     const int ksteps = __ldg(&p.kit[sl].x) >> 8;
-                    mbar_wait(halo_full, hg & 1);
-                    tc_fence_after();
-                    for (int tap = 0; tap < ntaps; ++tap, ++bg) {
-                        const int s = bg % BS;
-                        mbar_wait(&b_full[s], (bg / BS) & 1);
+                    for (int dx = 0; dx < ks; ++dx, ++sg) {
+                        const int sb = sg % HC::SLAB_BUFS;
+                        mbar_wait(&slab_full[sb], (sg / HC::SLAB_BUFS) & 1);
                         tc_fence_after();
-                        const int dy = tap / ks, dx = tap - dy * ks;
-                        const uint32_t aA = aHalo + (dy * HC::HALO_W + dx) * 128;
-                        const uint32_t aB = smem_u32(sB + s * HC::B_BYTES);
+                        const uint32_t aSlab = smem_u32(sSlab + sb * HC::SLAB_BYTES);
+                        for (int dy = 0; dy < ks; ++dy, ++bg) {
+                            const int s = bg % BS;
+                            mbar_wait(&b_full[s], (bg / BS) & 1);
+                            tc_fence_after();
+                            const uint32_t aA = aSlab + dy * HC::SLAB_W * 128;  // 1024-B aligned for every dy
+                            const uint32_t aB = smem_u32(sB + s * HC::B_BYTES);
 #pragma unroll 1
-                        for (int kk = 0; kk < ksteps; ++kk, ++g) {
-                            const uint64_t a_hi = umma_desc_sw128_halo(aA + kk * 32, HC::HALO_W * 128);
-                            const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                            if (NP == 2) {
-                                umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
-                                const uint64_t a_lo = umma_desc_sw128_halo(aA + plane_off + kk * 32, HC::HALO_W * 128);
-                                const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                                umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
-                                umma_f16(tmem_base + 2 * Cfg::ACC_STRIDE, a_hi, b_lo, idesc, 1u);
-                            } else {
-                                umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
+                            for (int kk = 0; kk < ksteps; ++kk, ++g) {
+                                const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
+                                const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
+                                if (NP == 2) {
+                                    if (Cfg::NACC == 3) umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
+                                    else umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
+                                    const uint64_t a_lo = umma_desc_sw128(aA + plane_off + kk * 32);
+                                    const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
+                                    umma_f16(tmem_base + cross, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
+                                    umma_f16(tmem_base + cross, a_hi, b_lo, idesc, 1u);
+                                } else {
+                                    umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
+                                }
                             }
+                            umma_commit(&b_empty[s]);
                         }
-                        umma_commit(&b_empty[s]);
+                        umma_commit(&slab_empty[sb]);  // frees the slab once its k taps have retired
                     }
-                    umma_commit(halo_empty);  // all taps of this slab have been issued; frees the halo when they retire
                 }
                 umma_commit(tmem_full_bar);
                 ++tile_i;

@@ -484,7 +484,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 const cuuint64_t C = t.C, W = t.W, H = t.H;
                 cuuint64_t dims[5] = {(cuuint64_t)(sp.c_begin + sp.c_count), W, H, (cuuint64_t)cap, (cuuint64_t)np};
                 cuuint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, static_cast<cuuint64_t>(cap) * H * W * C * 2};
-                cuuint32_t box[5] = {64, 16, (cuuint32_t)(16 + 2 * pad), 1, (cuuint32_t)np};
+                cuuint32_t box[5] = {64, 8, (cuuint32_t)(16 + 2 * pad), 1, (cuuint32_t)np};
                 encode(&rt.mapHalo[si], tensors[sp.tensor].buf.p, 5, dims, str, box);
             }
             if (c.srcs.size() < 2) rt.mapHalo[1] = rt.mapHalo[0];
@@ -753,7 +753,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
             P2P_CHECK(c.BN != 256 || persistent, "BN = 256 tiles need the persistent kernel");
-            if (use_halo && c.halo && (c.BN == 128 || c.BN == 64)) {
+            if (use_halo && c.halo) {
                 p.tw = 8; p.th = 16; p.nb = 1;
                 p.tiles_x = c.W / 8; p.tiles_y = c.H / 16;
                 p.grid_m = p.tiles_x * p.tiles_y * n; p.grid_z = 1;
@@ -763,10 +763,12 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
                 const int ctas = std::min<long long>(static_cast<long long>(p.grid_m) * p.grid_n, num_sms);
                 if (np == 2) {
-                    if (c.BN == 128) launch_conv_halo<128, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    if (c.BN == 256) launch_conv_halo<256, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    else if (c.BN == 128) launch_conv_halo<128, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
                     else launch_conv_halo<64, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
                 } else {
-                    if (c.BN == 128) launch_conv_halo<128, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    if (c.BN == 256) launch_conv_halo<256, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
+                    else if (c.BN == 128) launch_conv_halo<128, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
                     else launch_conv_halo<64, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
                 }
             } else if (persistent) {
