@@ -57,6 +57,13 @@ struct ConvParams {
     // Phase-fused transposed conv with a regular epilogue: accumulator column c = phase * fused_cout + channel,
     // phase (a,b) -> output pixel (2y+a, 2x+b).  0 = off.
     int fused_cout;
+    int tma_store;   // persistent kernel: stage 64-channel output slices in shared memory and write them with TMA stores
+                     // (the per-lane 16-byte stores of a row-per-thread epilogue are uncoalesced: 32 lines per instruction)
+    int single_acc;  // short K loops (<= 40 k16 steps): one TMEM accumulator instead of three (the round-toward-zero bias the
+                     // split guards against grows with the chain length; the epilogue drain is 3x cheaper)
+    int krot;        // (unused; experiment removed)
+    int dbg;         // bottleneck experiments on the persistent kernel (WRONG RESULTS): bit0 skip A loads, bit1 skip B loads,
+                     // bit2 MMA issuer does not wait for operands, bits 8.. = smem stages to use (0 = all)
     int halo_ksize;  // halo kernel (conv_tc_halo.cuh): kernel size; p.kit then holds the slab table, kstart[1] = #slabs
     int splitk_chunk;
     float* out_partial;
@@ -70,7 +77,9 @@ struct ConvCfg {
     static constexpr int B_BYTES = NP * BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int EPI_BYTES = NP * 128 * 128;  // output staging for the TMA-store epilogue (persistent kernel)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES_P = SMEM_BYTES + (BN >= 64 ? EPI_BYTES : 0);
     // fp16x3 keeps THREE accumulators in TMEM: two for the hi*hi products (even / odd k-steps) and one
     // for the 2^-11-times-smaller cross terms.  The tensor core rounds the fp32 accumulator toward zero
     // after every MMA; splitting the chains divides that bias (measured: resnet50 decode max error

@@ -30,7 +30,7 @@ struct HaloCfg {
 
 // slab table entry (p.kit): {map index | (k16 steps << 8), c0, first packed-weight k-iteration of (source, tap 0, chunk), chunks of the source}
 template <int BN, int NP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + kEpiThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                     const __grid_constant__ CUtensorMap mB, const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN, NP>;
@@ -76,7 +76,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
             mbar_init(&slab_empty[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 4);
+        mbar_init(tmem_empty_bar, kEpiWarps);
         fence_mbar_init();
     } else if (warp == 2) {
         tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -174,7 +174,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
             if (!tc.live) continue;
             mbar_wait(tmem_full_bar, tile_i & 1);
             tc_fence_after();
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit, nullptr, nullptr, static_cast<int>(threadIdx.x) - 64);
             ++tile_i;
         }
     }

@@ -43,31 +43,47 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int
     return c;
 }
 
-// Epilogue of one tile for one epilogue thread (TMEM lane = accumulator row): drains the accumulators into
-// registers (summing the three fp16x3 accumulators), releases TMEM to the MMA warp, then applies folded BN /
-// bias / residual / activation, splits into fp16 hi/lo and stores NHWC.  Shared by the persistent kernels.
+// Epilogue of one tile.  kEpiWarps = 8 warps (256 threads): warp w may only touch TMEM lanes (w % 4) * 32 .. + 31, so
+// two warps share each 32-row quarter and split the COLUMNS: of every 64-channel slice, group h (= warps 2-5 / 6-9)
+// takes the 32 columns h*32 .. h*32+31.  Per tile each thread (a) drains its columns of the (up to three) accumulators
+// into registers, (b) releases TMEM to the MMA warp, (c) applies folded BN / bias / residual / activation and the hi/lo
+// split, (d) stages the 64-channel slice in a swizzled shared-memory tile that one thread writes out with a TMA store
+// (direct global stores for the split-K, heads and BN < 64 paths).  Eight warps, not four: the epilogue is
+// latency-bound (residual / scale loads) and with one warp per scheduler nothing hides that latency.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+
 template <int BN, int NP>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_empty_bar,
-                                              const TileCoord& tc, int hl, int wl, int nl, int n_limit) {
+                                              const TileCoord& tc, int hl, int wl, int nl, int n_limit, uint8_t* stage,
+                                              const CUtensorMap* const* omaps, int etid) {
     using Cfg = ConvCfg<BN, NP>;
-    constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns drained per pass
+    constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns handled per pass (all threads)
     constexpr int NPASS = BN > 128 ? BN / 128 : 1;
+    constexpr int NSL = NCOL >= 64 ? NCOL / 64 : 1;               // 64-channel slices per pass
+    constexpr int MYC = BN >= 64 ? 32 * NSL : NCOL;               // columns this thread owns per pass
+    const int h = etid >> 7;                                     // column group
     const bool splitk = p.splitk_chunk > 0;
     const int z = tc.z, zi = splitk ? 0 : z;
+    const int y = tc.y0 + hl, x = tc.x0 + wl, n = tc.n0 + nl;
+    const bool valid = (y < p.H) && (x < p.W) && (n < n_limit);
+    const int oy = y * p.sy + p.oy_off[zi], ox = x * p.sx + p.ox_off[zi];
+    const long long pix = (static_cast<long long>(n) * p.OH + oy) * p.OW + ox;
+    const bool tstore = BN >= 64 && p.tma_store && !splitk && p.act != ACT_HEADS;
+    const bool nacc3 = Cfg::NACC == 3 && !p.single_acc, nacc2 = Cfg::NACC >= 2 && !p.single_acc;
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass) {
-    const uint32_t tcol = taddr + pass * NCOL;
-    __syncwarp();  // lanes may arrive here diverged (per-lane store paths of the previous tile); tcgen05.ld is .aligned
-    do {
-            // ---- drain TMEM into registers, summing the fp16x3 accumulators
-            float acc[NCOL];
-            if (BN < 32) {
+        __syncwarp();  // lanes may arrive diverged (per-lane paths of the previous tile); tcgen05.ld is .aligned
+        float acc[MYC];
+        if (BN < 64) {
+            // small tiles (heads BN = 16): group 0 does all the work
+            if (h == 0) {
                 uint32_t v[16];
                 tmem_ld_32x16(taddr, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-                if (Cfg::NACC == 3) {
+                if (nacc3) {
                     uint32_t v1[16], v2[16];
                     tmem_ld_32x16(taddr + Cfg::ACC_STRIDE, v1);
                     tmem_ld_32x16(taddr + 2 * Cfg::ACC_STRIDE, v2);
@@ -75,112 +91,139 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = (acc[j] + __uint_as_float(v1[j])) + __uint_as_float(v2[j]);
                 }
-            } else {
+            }
+        } else {
 #pragma unroll
-                for (int ch = 0; ch < NCOL / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tcol + ch * 32, v);
+            for (int sl = 0; sl < NSL; ++sl) {
+                const uint32_t tcol = taddr + pass * NCOL + sl * 64 + h * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(tcol, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[sl * 32 + j] = __uint_as_float(v[j]);
+                if (nacc2) {
+                    tmem_ld_32x32(tcol + Cfg::ACC_STRIDE, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[ch * 32 + j] = __uint_as_float(v[j]);
-                    if (Cfg::NACC >= 2) {
-                        tmem_ld_32x32(tcol + Cfg::ACC_STRIDE + ch * 32, v);
-                        tmem_ld_wait();
+                    for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
+                }
+                if (nacc3) {
+                    tmem_ld_32x32(tcol + 2 * Cfg::ACC_STRIDE, v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[ch * 32 + j] += __uint_as_float(v[j]);
-                    }
-                    if (Cfg::NACC == 3) {
-                        tmem_ld_32x32(tcol + 2 * Cfg::ACC_STRIDE + ch * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[ch * 32 + j] += __uint_as_float(v[j]);
-                    }
+                    for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
                 }
             }
-            if (pass == NPASS - 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty_bar);  // TMEM is free: the next tile's MMAs may start
-            }
+        }
+        if (pass == NPASS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);  // TMEM is free: the next tile's MMAs may start
+        }
 
-            // ---- BN / bias / residual / activation / hi-lo split / stores, from registers
-            const int y = tc.y0 + hl, x = tc.x0 + wl, n = tc.n0 + nl;
-            const bool valid = (y < p.H) && (x < p.W) && (n < n_limit);
-            if (!valid) break;
-            const int oy = y * p.sy + p.oy_off[zi], ox = x * p.sx + p.ox_off[zi];
-            const long long pix = (static_cast<long long>(n) * p.OH + oy) * p.OW + ox;
-            if (p.act == ACT_HEADS) {
-                if (BN < 32) {
+        if (BN < 64) {
+            if (h == 0 && valid && p.act == ACT_HEADS) {
 #pragma unroll
-                    for (int ph = 0; ph < 4; ++ph) {
-                        const long long opix = (static_cast<long long>(n) * p.OH + (2 * y + (ph >> 1))) * p.OW + (2 * x + (ph & 1));
-                        float* d = p.out_dec + opix * 3;
+                for (int ph = 0; ph < 4; ++ph) {
+                    const long long opix = (static_cast<long long>(n) * p.OH + (2 * y + (ph >> 1))) * p.OW + (2 * x + (ph & 1));
+                    float* d = p.out_dec + opix * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            d[c] = tanhf(acc[ph * 4 + c] * __ldg(&p.scale[ph * 4 + c]) + __ldg(&p.shift[ph * 4 + c]));
-                        const float e = acc[ph * 4 + 3] * __ldg(&p.scale[ph * 4 + 3]) + __ldg(&p.shift[ph * 4 + 3]);
-                        p.out_prob[opix] = 1.f / (1.f + expf(-e));
-                    }
-                }
-                break;
-            }
-            if (BN >= 32) {
-#pragma unroll
-                for (int ch = 0; ch < NCOL / 32; ++ch) {
-                    const int c0 = tc.nt0 + pass * NCOL + ch * 32;
-                    if (splitk) {
-                        float4* dst = reinterpret_cast<float4*>(p.out_partial + z * p.partial_stride + pix * p.Cout_pad + c0);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            dst[g] = make_float4(acc[ch * 32 + 4 * g], acc[ch * 32 + 4 * g + 1], acc[ch * 32 + 4 * g + 2], acc[ch * 32 + 4 * g + 3]);
-                        continue;
-                    }
-                    if (c0 >= p.Cout) continue;
-                    long long opix = pix;
-                    int cch = c0;
-                    if (p.fused_cout) {
-                        const int phs = c0 / p.fused_cout;
-                        cch = c0 - phs * p.fused_cout;
-                        opix = (static_cast<long long>(n) * p.OH + (2 * y + (phs >> 1))) * p.OW + (2 * x + (phs & 1));
-                    }
-                    __half* o_hi = p.out_hi + opix * p.Ctot + p.c_off + cch;
-                    const __half* r_hi = p.res_hi ? p.res_hi + opix * p.res_Ctot + cch : nullptr;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
-                        if (r_hi) {
-                            rh = __ldg(reinterpret_cast<const uint4*>(r_hi + g * 8));
-                            if (p.res_plane) rl = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + g * 8));
-                        }
-                        const __half* rhh = reinterpret_cast<const __half*>(&rh);
-                        const __half* rlh = reinterpret_cast<const __half*>(&rl);
-                        uint4 oh, ol;
-                        __half* ohh = reinterpret_cast<__half*>(&oh);
-                        __half* olh = reinterpret_cast<__half*>(&ol);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c = c0 + g * 8 + j;
-                            float val = acc[ch * 32 + g * 8 + j] * __ldg(&p.scale[c]) + __ldg(&p.shift[c]);
-                            if (r_hi) val += __half2float(rhh[j]) + __half2float(rlh[j]);
-                            val = act_apply(val, p.act);
-                            const __half h = __float2half_rn(val);
-                            ohh[j] = h;
-                            olh[j] = __float2half_rn(val - __half2float(h));
-                        }
-                        *reinterpret_cast<uint4*>(o_hi + g * 8) = oh;
-                        if (p.out_plane) *reinterpret_cast<uint4*>(o_hi + p.out_plane + g * 8) = ol;
-                    }
+                    for (int c = 0; c < 3; ++c)
+                        d[c] = tanhf(acc[ph * 4 + c] * __ldg(&p.scale[ph * 4 + c]) + __ldg(&p.shift[ph * 4 + c]));
+                    const float e = acc[ph * 4 + 3] * __ldg(&p.scale[ph * 4 + 3]) + __ldg(&p.shift[ph * 4 + 3]);
+                    p.out_prob[opix] = 1.f / (1.f + expf(-e));
                 }
             }
-    } while (false);
+            continue;
+        }
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+            const int c0s = tc.nt0 + pass * NCOL + sl * 64;  // first channel of the 64-wide slice
+            const int c0 = c0s + h * 32;                     // first of this thread's 32 channels
+            if (splitk) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(p.out_partial + z * p.partial_stride + pix * p.Cout_pad + c0);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        dst[g] = make_float4(acc[sl * 32 + 4 * g], acc[sl * 32 + 4 * g + 1], acc[sl * 32 + 4 * g + 2], acc[sl * 32 + 4 * g + 3]);
+                }
+                continue;
+            }
+            if (c0s >= p.Cout) continue;  // uniform over the CTA
+            int phs = 0, cch = c0;
+            long long opix = pix;
+            if (p.fused_cout) {
+                phs = c0s / p.fused_cout;
+                cch = c0 - phs * p.fused_cout;
+                opix = (static_cast<long long>(n) * p.OH + (2 * y + (phs >> 1))) * p.OW + (2 * x + (phs & 1));
+            }
+            const __half* r_hi = (p.res_hi && valid) ? p.res_hi + opix * p.res_Ctot + cch : nullptr;
+            __half* o_hi = p.out_hi + opix * p.Ctot + p.c_off + cch;
+            const int r = (nl * p.th + hl) * p.tw + wl;  // MMA row == row of the staging box
+            if (tstore) {
+                if (etid == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
+                named_bar_sync(1, kEpiThreads);
+            }
+            // residual and scale / shift loads first (independent), then the arithmetic
+            uint4 rh[4], rl[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                rh[g] = make_uint4(0, 0, 0, 0); rl[g] = make_uint4(0, 0, 0, 0);
+                if (r_hi) {
+                    rh[g] = __ldg(reinterpret_cast<const uint4*>(r_hi + g * 8));
+                    if (p.res_plane) rl[g] = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + g * 8));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float sc8[8], sh8[8];
+                *reinterpret_cast<float4*>(sc8) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8));
+                *reinterpret_cast<float4*>(sc8 + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8 + 4));
+                *reinterpret_cast<float4*>(sh8) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8));
+                *reinterpret_cast<float4*>(sh8 + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8 + 4));
+                const __half* rhh = reinterpret_cast<const __half*>(&rh[g]);
+                const __half* rlh = reinterpret_cast<const __half*>(&rl[g]);
+                uint4 oh, ol;
+                __half* ohh = reinterpret_cast<__half*>(&oh);
+                __half* olh = reinterpret_cast<__half*>(&ol);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float val = acc[sl * 32 + g * 8 + j] * sc8[j] + sh8[j];
+                    if (r_hi) val += __half2float(rhh[j]) + __half2float(rlh[j]);
+                    val = act_apply(val, p.act);
+                    const __half hv = __float2half_rn(val);
+                    ohh[j] = hv;
+                    olh[j] = __float2half_rn(val - __half2float(hv));
+                }
+                if (tstore) {
+                    const uint32_t c16 = static_cast<uint32_t>(h * 4 + g);  // 16-byte chunk inside the 128-byte row
+                    const uint32_t off = static_cast<uint32_t>(r) * 128 + ((c16 ^ (static_cast<uint32_t>(r) & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(stage + off) = oh;
+                    if (NP == 2) *reinterpret_cast<uint4*>(stage + 128 * 128 + off) = ol;
+                } else if (valid) {
+                    *reinterpret_cast<uint4*>(o_hi + g * 8) = oh;
+                    if (p.out_plane) *reinterpret_cast<uint4*>(o_hi + p.out_plane + g * 8) = ol;
+                }
+            }
+            if (tstore) {
+                fence_proxy_async();
+                named_bar_sync(1, kEpiThreads);
+                if (etid == 0) {
+                    tma_store_5d(omaps[p.sy == 2 ? (p.fused_cout ? phs : z) : 0], stage, p.c_off + (cch - h * 32), tc.x0, tc.y0, tc.n0, 0);
+                    bulk_commit_group();
+                }
+            }
+        }
     }
 }
 
 template <int BN, int NP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + kEpiThreads, 1)
 conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                           const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
-                          const __grid_constant__ CUtensorMap mB, const __grid_constant__ ConvParams p) {
+                          const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO0,
+                          const __grid_constant__ CUtensorMap mO1, const __grid_constant__ CUtensorMap mO2,
+                          const __grid_constant__ CUtensorMap mO3, const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN, NP>;
     constexpr int STAGES = Cfg::STAGES;
     const int warp = threadIdx.x >> 5;
@@ -195,7 +238,8 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;  // output staging (BN >= 64), 1024-B aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + (BN >= 64 ? Cfg::EPI_BYTES : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 1;
@@ -209,7 +253,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 4);  // one arrival per epilogue warp
+        mbar_init(tmem_empty_bar, kEpiWarps);  // one arrival per epilogue warp
         fence_mbar_init();
     } else if (warp == 2) {
         tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -219,6 +263,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    const int nst = (p.dbg >> 8) > 0 && (p.dbg >> 8) < STAGES ? (p.dbg >> 8) : STAGES;
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -227,17 +272,19 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                 const TileCoord tc = decode_tile<BN>(p, t, n_limit);
                 if (!tc.live) continue;
                 for (int it = 0; it < tc.nk; ++it, ++itg) {
-                    const int s = itg % STAGES;
-                    const uint32_t ph = (itg / STAGES) & 1;
+                    const int s = itg % nst;
+                    const uint32_t ph = (itg / nst) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     const int4 k = __ldg(&p.kit[tc.kbeg + it]);
                     uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    const uint32_t tx = ((p.dbg & 1) ? 0 : Cfg::A_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
+                    if (tx == 0) { mbar_arrive(&full_bar[s]); continue; }
+                    mbar_arrive_expect_tx(&full_bar[s], tx);
                     const int mi = k.x & 0xff;
                     const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
-                    tma_load_5d(mA, &full_bar[s], sA, k.w, tc.x0 + k.z, tc.y0 + k.y, tc.n0, 0);
-                    tma_load_4d(&mB, &full_bar[s], sB, 0, tc.nt0, 0, tc.kbeg + it);
+                    if (!(p.dbg & 1)) tma_load_5d(mA, &full_bar[s], sA, k.w, tc.x0 + k.z, tc.y0 + k.y, tc.n0, 0);
+                    if (!(p.dbg & 2)) tma_load_4d(&mB, &full_bar[s], sB, 0, tc.nt0, 0, tc.kbeg + it);
                 }
             }
         }
@@ -253,10 +300,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                 tc_fence_after();
                 int g = 0;
                 for (int it = 0; it < tc.nk; ++it, ++itg) {
-                    const int s = itg % STAGES;
-                    const uint32_t ph = (itg / STAGES) & 1;
+                    const int s = itg % nst;
+                    const uint32_t ph = (itg / nst) & 1;
                     const int ksteps = __ldg(&p.kit[tc.kbeg + it].x) >> 8;
-                    mbar_wait(&full_bar[s], ph);
+                    if (!(p.dbg & 4)) mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t aA = smem_u32(smem + s * Cfg::STAGE_BYTES);
                     const uint32_t aB = aA + Cfg::A_BYTES;
@@ -265,12 +312,12 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                         const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
                         const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
                         if (NP == 2) {
-                            constexpr uint32_t cross = (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
-                            if (Cfg::NACC == 3) umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
+                            const uint32_t cross = p.single_acc ? 0u : (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
+                            if (Cfg::NACC == 3 && !p.single_acc) umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
                             else umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                             const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
                             const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, g > 0 ? 1u : 0u);
+                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, (g > 0 || p.single_acc) ? 1u : 0u);
                             umma_f16(tmem_base + cross, a_hi, b_lo, idesc, 1u);
                         } else {
                             umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
@@ -290,15 +337,18 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         const int hl = (r / p.tw) % p.th;
         const int nl = r / (p.tw * p.th);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const CUtensorMap* const omaps[4] = {&mO0, &mO1, &mO2, &mO3};
         int tile_i = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
             mbar_wait(tmem_full_bar, tile_i & 1);
             tc_fence_after();
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit, BN >= 64 ? sEpi : nullptr, omaps,
+                                  static_cast<int>(threadIdx.x) - 64);
             ++tile_i;
         }
+        if (threadIdx.x == 64) bulk_wait_all();  // outstanding TMA stores complete before the CTA retires
     }
 
     tc_fence_before();

@@ -425,6 +425,9 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
     if (const char* e = getenv("P2P_HALO")) use_halo = atoi(e) != 0;
+    if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
+    if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
+    if (const char* e = getenv("P2P_KROT")) krot = atoi(e) != 0;
 
     tensors.resize(plan.tensors.size());
     for (size_t i = 0; i < plan.tensors.size(); ++i) {
@@ -474,6 +477,35 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
             encode(&rt.mapA[mi], base, 5, dims, str, box);
         }
         for (size_t mi = c.maps.size(); mi < 4; ++mi) rt.mapA[mi] = rt.mapA[0];
+        memset(rt.mapOut, 0, sizeof(rt.mapOut));
+        rt.has_out = false;
+        if (c.act != ACT_HEADS && c.splitk <= 1 && c.out_tensor >= 0 && c.BN >= 64) {
+            const TensorSpec& to = plan.tensors[c.out_tensor];
+            __half* obase = tensors[c.out_tensor].buf.p;
+            const cuuint64_t OC = to.C, OW = to.W, OH = to.H;
+            const cuuint64_t oplane_b = static_cast<cuuint64_t>(cap) * OH * OW * OC * 2;
+            cuuint32_t box[5] = {64, (cuuint32_t)c.tw, (cuuint32_t)c.th, (cuuint32_t)c.nb, (cuuint32_t)np};
+            if (c.kind == K_DENSE) {
+                const cuuint64_t K = OH * OW * OC;
+                cuuint64_t dims[5] = {K, 1, 1, (cuuint64_t)cap, (cuuint64_t)np};
+                cuuint64_t str[4] = {K * 2, K * 2, K * 2, oplane_b};
+                encode(&rt.mapOut[0], obase, 5, dims, str, box);
+                for (int i = 1; i < 4; ++i) rt.mapOut[i] = rt.mapOut[0];
+            } else if (c.sy == 1) {
+                cuuint64_t dims[5] = {OC, OW, OH, (cuuint64_t)cap, (cuuint64_t)np};
+                cuuint64_t str[4] = {OC * 2, OW * OC * 2, OH * OW * OC * 2, oplane_b};
+                encode(&rt.mapOut[0], obase, 5, dims, str, box);
+                for (int i = 1; i < 4; ++i) rt.mapOut[i] = rt.mapOut[0];
+            } else {
+                for (int ph = 0; ph < 4; ++ph) {  // output pixel (2y+a, 2x+b): strided view of the output tensor
+                    const int a = ph >> 1, b = ph & 1;
+                    cuuint64_t dims[5] = {OC, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)cap, (cuuint64_t)np};
+                    cuuint64_t str[4] = {2 * OC * 2, 2 * OW * OC * 2, OH * OW * OC * 2, oplane_b};
+                    encode(&rt.mapOut[ph], obase + (static_cast<size_t>(a) * OW + b) * OC, 5, dims, str, box);
+                }
+            }
+            rt.has_out = true;
+        }
         memset(rt.mapHalo, 0, sizeof(rt.mapHalo));
         if (c.halo) {
             rt.slabs.upload(c.slabs.data(), c.slabs.size());
@@ -645,14 +677,15 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
 namespace {
 
 template <int BN, int NP>
-void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const ConvParams& p, int ctas, cudaStream_t s) {
+void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap* mO, const ConvParams& p, int ctas,
+                            cudaStream_t s) {
     using Cfg = ConvCfg<BN, NP>;
     static bool configured = false;
     if (!configured) {
-        P2P_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        P2P_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES_P));
         configured = true;
     }
-    conv_tc_persistent_kernel<BN, NP><<<ctas, 192, Cfg::SMEM_BYTES, s>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
+    conv_tc_persistent_kernel<BN, NP><<<ctas, 64 + kEpiThreads, Cfg::SMEM_BYTES_P, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO[0], mO[1], mO[2], mO[3], p);
     P2P_CUDA(cudaGetLastError());
 }
 
@@ -664,7 +697,7 @@ void launch_conv_halo(const CUtensorMap* mH, const CUtensorMap& mB, const ConvPa
         P2P_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, HC::SMEM_BYTES));
         configured = true;
     }
-    conv_tc_halo_kernel<BN, NP><<<ctas, 192, HC::SMEM_BYTES, s>>>(mH[0], mH[1], mB, p);
+    conv_tc_halo_kernel<BN, NP><<<ctas, 64 + kEpiThreads, HC::SMEM_BYTES, s>>>(mH[0], mH[1], mB, p);
     P2P_CUDA(cudaGetLastError());
 }
 
@@ -742,6 +775,19 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 p.res_Ctot = plan.tensors[c.res_tensor].C;
             }
             p.n_active = n_active;
+            p.krot = 0;
+            {
+                int max_steps = 0;   // longest accumulation chain of this launch, in k16 steps
+                const int nz = c.splitk > 1 ? 1 : c.phases;
+                for (int z = 0; z < nz; ++z) {
+                    int steps = 0;
+                    const int kb = c.kstart[z], ke = c.splitk > 1 ? std::min<int>(c.splitk_chunk, static_cast<int>(c.kit.size())) : c.kstart[z + 1];
+                    for (int it = kb; it < ke; ++it) steps += c.kit[it].x >> 8;
+                    max_steps = std::max(max_steps, steps);
+                }
+                p.single_acc = (persistent && np == 2 && max_steps <= single_acc_steps) ? 1 : 0;
+            }
+            if (const char* e = getenv("P2P_DBG")) p.dbg = atoi(e);
             p.Cout_pad = c.Cout_pad;
             if (c.kind == K_CONVT_FUSED && c.act != ACT_HEADS) p.fused_cout = c.Cout / 4;
             if (c.splitk > 1) {
@@ -772,18 +818,19 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     else launch_conv_halo<64, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
                 }
             } else if (persistent) {
+                p.tma_store = (tma_store && rt.has_out) ? 1 : 0;
                 const int ctas = std::min<long long>(static_cast<long long>(grid.x) * grid.y * grid.z, num_sms);
                 if (c.BN == 256) {
-                    if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, p, ctas, s);
-                    else launch_conv_persistent<256, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                    if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    else launch_conv_persistent<256, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
                 } else if (np == 2) {
-                    if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, p, ctas, s);
-                    else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, p, ctas, s);
-                    else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, p, ctas, s);
+                    if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
                 } else {
-                    if (c.BN == 128) launch_conv_persistent<128, 1>(rt.mapA, mc.mapB, p, ctas, s);
-                    else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, p, ctas, s);
-                    else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, p, ctas, s);
+                    if (c.BN == 128) launch_conv_persistent<128, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
                 }
             } else if (np == 2) {
                 if (c.BN == 128) launch_conv<128, 2>(rt.mapA, mc.mapB, p, grid, s);

@@ -41,7 +41,34 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mode, int feed_kb
     tc_fence_after();
     const uint32_t tm = *slot;
     constexpr uint32_t idesc = umma_idesc_f16(128, N);
-    if (threadIdx.x == 0) {
+    if (mode >= 10 && threadIdx.x < 32) {
+        // warp-uniform control flow, MMAs issued inside elect.sync (the CUTLASS / DeepGEMM idiom)
+        const int m = mode - 10;
+        const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t a_hi = umma_desc_sw128(aA + kk * 32), b_hi = umma_desc_sw128(aB + kk * 32);
+                    if (m == 0) {
+                        umma_f16(tm, a_hi, b_hi, idesc, 1u);
+                    } else {
+                        const uint64_t a_lo = umma_desc_sw128(aA + 16384 + kk * 32), b_lo = umma_desc_sw128(aB + N * 128 + kk * 32);
+                        umma_f16(tm, a_hi, b_hi, idesc, 1u);
+                        umma_f16(tm + 256, a_lo, b_hi, idesc, 1u);
+                        umma_f16(tm + 256, a_hi, b_lo, idesc, 1u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+        mbar_wait(bar, 0);
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    } else if (mode < 10 && threadIdx.x == 0) {
         const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
@@ -64,7 +91,7 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mode, int feed_kb
         mbar_wait(bar, 0);
         const long long t1 = clock64();
         out[blockIdx.x] = t1 - t0;
-    } else if (threadIdx.x == 32 && feed_kb_per_iter > 0) {
+    } else if (threadIdx.x == 32 && feed_kb_per_iter > 0 && mode < 10) {
         // emulate the TMA operand feed: feed_kb_per_iter KB of bulk copies per "k-iteration"
         const long long t0 = clock64();
         const int per_mma = mode == 1 ? 12 : 4;
@@ -95,7 +122,7 @@ void run(const char* name, int mode, int feed, const uint8_t* gsrc, long long* d
     cudaMemcpy(h, dout, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
     long long mx = 0, sum = 0;
     for (int i = 0; i < sms; ++i) { mx = h[i] > mx ? h[i] : mx; sum += h[i]; }
-    const double mmas = static_cast<double>(iters) * (mode == 1 ? 12 : 4);
+    const double mmas = static_cast<double>(iters) * ((mode % 10) == 1 ? 12 : 4);
     printf("%-44s N=%3d feed %2d KB/iter : %.1f cycles/MMA (avg over SMs), %.1f (slowest SM); ideal %d\n", name, N, feed, sum / (double)sms / mmas,
            mx / mmas, N / 2);
 }
@@ -107,12 +134,16 @@ int main() {
     cudaMalloc(&gsrc, static_cast<size_t>(sms) * 64 * 1024);
     cudaMemset(gsrc, 0, static_cast<size_t>(sms) * 64 * 1024);
     cudaMalloc(&dout, sizeof(long long) * 256);
-    for (int feed : {0, 32, 64, 96}) {
+    for (int feed : {0, 64}) {
         run<128>("SS, 1 MMA per k-step", 0, feed == 0 ? 0 : feed / 2, gsrc, dout, sms);
         run<128>("SS, fp16x3 pattern (3 MMAs per k-step)", 1, feed, gsrc, dout, sms);
         run<256>("SS, 1 MMA per k-step", 0, feed == 0 ? 0 : feed / 2, gsrc, dout, sms);
         run<256>("SS, fp16x3 pattern", 1, feed, gsrc, dout, sms);
     }
+    run<128>("SS elect.sync idiom, 1 MMA per k-step", 10, 0, gsrc, dout, sms);
+    run<128>("SS elect.sync idiom, fp16x3 pattern", 11, 0, gsrc, dout, sms);
+    run<256>("SS elect.sync idiom, 1 MMA per k-step", 10, 0, gsrc, dout, sms);
+    run<256>("SS elect.sync idiom, fp16x3 pattern", 11, 0, gsrc, dout, sms);
     run<128>("TS (A in TMEM), 1 MMA per k-step", 2, 0, gsrc, dout, sms);
     run<256>("TS (A in TMEM), 1 MMA per k-step", 2, 0, gsrc, dout, sms);
     return 0;
