@@ -49,7 +49,7 @@ __device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t,
 }
 
 // ---- (1) hypotheses: RNG replay by thread 0, then one 5-point EPnP per thread
-__global__ void __launch_bounds__(kHypThreads) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
+__global__ void __launch_bounds__(kHypThreads, 4) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
                                                                  const float* __restrict__ obj, const float* __restrict__ img,
                                                                  double* __restrict__ hyp, int iters) {
     extern __shared__ int s_idx[];
@@ -199,7 +199,7 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red, double* s
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRefitThreads) epnp_refit_kernel(const PnpProblem* __restrict__ probs,
+__global__ void __launch_bounds__(kRefitThreads, 2) epnp_refit_kernel(const PnpProblem* __restrict__ probs,
                                                                    const float* __restrict__ obj, const float* __restrict__ img,
                                                                    const uint8_t* __restrict__ mask, PnpResult* __restrict__ res) {
     __shared__ double s_red[(kRefitThreads / 32) * 52];
