@@ -154,6 +154,8 @@ def run_ours(args):
     import ctypes
     from pix2pose_b200 import _lib, dist as D, weights as Wt
     from pix2pose_b200.recognition import _Det, _Pose, pix2pose
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version banner there)
     rank, local_rank, world = D.init()
     frames, rois, fids = workload(rank)
     n_det = len(rois)
@@ -217,6 +219,7 @@ def run_ours(args):
     d2h = int(n_det * ctypes.sizeof(_Pose))
 
     if rank != 0:
+        D.shutdown()
         return
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv), measured live
     x = np.random.RandomState(0).uniform(-1, 1, (args.capacity, 128, 128, 3)).astype(np.float32)
@@ -258,6 +261,7 @@ def run_ours(args):
                                    "Keras/TF-CPU) + numpy resize + real cv2.solvePnPRansac (%d threads)" % (args.cpu_sample, cpu_dt, cores, cvthreads)},
     }
     print(json.dumps(out))
+    D.shutdown()
 
 
 def main():

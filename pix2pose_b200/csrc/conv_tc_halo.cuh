@@ -2,15 +2,18 @@
 // deconv1/2/3 of the decoder (66 % of the network's FLOPs, ae_model.py:209, 218, 228) and the 3x3
 // convs of the ResNet bottlenecks (resnet50_mod.py:62-65).
 //
-// Why: the generic kernel is shared-memory-bandwidth bound (profiles/r01_summary.md).  Each 128x128x16 MMA
-// reads 8 KB of operands from smem in 64 cycles -- the full 128 B/cycle -- and the TMA writes that feed it
-// (A 32 KB + B 32 KB per 12 MMAs = 5.3 KB per MMA) compete for the same port: 13.3 KB / 128 B/clk = 104 cycles
-// per MMA, i.e. the measured 66 % tensor-pipe utilisation.  This kernel removes most of the A writes: the output
-// tile is 8 (w) x 16 (h) pixels, and for each 64-channel chunk and each horizontal tap offset dx ONE slab of
-// 8 x (16 + 2*pad) pixels is loaded; the k vertical taps dy are then plain descriptor offsets into it
-// (MMA row r = h*8 + w  <->  slab pixel dy*8 + r: contiguous 128-byte rows, start 1024-B aligned for every dy,
-// so the ordinary K-major SWIZZLE_128B descriptor applies).  A traffic drops by k (5x for 5x5), weights stream
-// per tap as before.
+// Idea: the generic kernel re-fetches the 128-pixel activation tile for every tap (25 shifted copies for 5x5, all L2
+// hits).  Here the output tile is 8 (w) x 16 (h) pixels, and for each 64-channel chunk and each horizontal tap offset dx
+// ONE slab of 8 x (16 + 2*pad) pixels is loaded; the k vertical taps dy are then plain descriptor offsets into it
+// (MMA row r = h*8 + w  <->  slab pixel dy*8 + r: contiguous 128-byte rows, start 1024-B aligned for every dy, so the
+// ordinary K-major SWIZZLE_128B descriptor applies -- a first version that also shifted by dx inside a 16-wide slab
+// produced wrong results: an 8-row core-matrix group may not straddle a 1024-byte swizzle atom).  Activation traffic
+// drops by k (5x for 5x5); weights stream per tap as before.
+//
+// Status: bit-for-bit as accurate as the generic kernel (decode max error 8.5e-5), but NOT faster (11.32 vs 11.25 ms per
+// 256-crop forward): the experiments in profiles/r01_summary.md show that the big convolutions are bound by the tensor
+// pipe's instruction rate, not by operand supply.  Kept behind P2P_HALO=1 as the starting point for an N = 256 /
+// cta_group::2 version where the freed shared memory matters.
 #pragma once
 #include "conv_tc_persistent.cuh"
 

@@ -29,7 +29,9 @@ def init(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     elif world == 1 and torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
     if torch.cuda.is_available():
@@ -37,6 +39,12 @@ def init(backend=None):
         from . import _lib
         _lib.check(_lib.lib().p2p_set_device(local_rank))
     return rank, local_rank, world
+
+
+def shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier():
