@@ -142,3 +142,30 @@ def test_multi_object_stream_matches_per_object_calls(frame):
         assert one.status[0] == status[i]
         assert np.array_equal(one.R[0].ravel(), rec[i, :9]) and np.array_equal(one.t[0], rec[i, 9:12])
     assert len({tuple(rec[0, :9]), tuple(rec[1, :9])}) == 2
+
+
+def test_evaluation_loop_batched_equals_per_roi(frame):
+    """the per-image loop of tools/5_evaluation_bop_basic.py:281-349 with the per-object device batches
+    gives exactly the rows the reference-style one-est_pose-per-ROI loop gives (same recognisers, same detections)."""
+    from pix2pose_b200 import evaluation as E
+    from pix2pose_b200.recognition import pix2pose
+    targets, inst_counts = [3, 7], [2, 1]
+    objs = {3: np.array([50., 40., 60., 0., 0., 0.]), 7: np.array([30., 30., 80., 1., -2., 3.])}
+    recs = [pix2pose(W.synthetic_weights("paper", s), K_LM, 640, 480, objs[o], backbone="paper", capacity=16, max_dets=16,
+                     th_outlier=[0.15, 0.25, 0.35], th_inlier=0.15) for o, s in ((3, 1), (7, 2))]
+    rng = np.random.RandomState(5)
+    rois, oids = [], []
+    for i in range(9):
+        cy, cx, h, w = rng.randint(80, 400), rng.randint(80, 560), rng.randint(50, 120), rng.randint(50, 120)
+        rois.append([cy - h // 2, cx - w // 2, cy + h // 2, cx + w // 2]); oids.append([3, 7, 11][i % 3])
+    rois[2] = [-1, -1, 4, 4]
+    orders = [targets.index(o) if o in targets else 0 for o in oids]
+    scores = rng.uniform(0.5, 1, 9)
+    masks = np.zeros((480, 640, 9), bool)
+    for i, r in enumerate(rois):
+        masks[max(r[0], 0):r[2], max(r[1], 0):r[3], i] = True
+    a = E.recognize_image(recs, frame, rois, orders, oids, scores, masks, targets, inst_counts, K_LM, backend=E.est_pose_batched)
+    b = E.recognize_image(recs, frame, rois, orders, oids, scores, masks, targets, inst_counts, K_LM, backend=E.est_pose_loop)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x["obj_id"] == y["obj_id"] and x["score"] == y["score"] and np.array_equal(x["R"], y["R"]) and np.array_equal(x["t"], y["t"])
