@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpix2pose_b200.so")
+LIB_PATH = os.environ.get("P2P_LIB", os.path.join(_HERE, "libpix2pose_b200.so"))   # P2P_LIB: A/B experiments with another build
 
 P2P_OK = 0
 PREC_FP16X3 = 0

@@ -61,14 +61,18 @@ struct ConvParams {
                      // (the per-lane 16-byte stores of a row-per-thread epilogue are uncoalesced: 32 lines per instruction)
     int single_acc;  // short K loops (<= 40 k16 steps): one TMEM accumulator instead of three (the round-toward-zero bias the
                      // split guards against grows with the chain length; the epilogue drain is 3x cheaper)
-    int krot;        // (unused; experiment removed)
+    int nst;         // persistent kernel: operand stages to use (0 = all).  Short-K layers run on fewer stages and hand the
+    int epi_bufs;    // top ones to the epilogue as extra output staging tiles (epi_bufs = 1..3 tiles of EPI_BYTES)
     int dbg;         // bottleneck experiments on the persistent kernel (WRONG RESULTS): bit0 skip A loads, bit1 skip B loads,
-                     // bit2 MMA issuer does not wait for operands, bits 8.. = smem stages to use (0 = all)
+                     // bit2 MMA issuer does not wait for operands
     int halo_ksize;  // halo kernel (conv_tc_halo.cuh): kernel size; p.kit then holds the slab table, kstart[1] = #slabs
     int splitk_chunk;
     float* out_partial;
     long long partial_stride;  // elements between K slices
     int Cout_pad;
+    // k16 steps of every k-iteration (same numbers as kit[i].x >> 8), in the kernel parameters so that the MMA issuer
+    // reads them through the constant bank into uniform registers
+    uint8_t ksteps_tab[512];
 };
 
 template <int BN, int NP>

@@ -171,13 +171,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
         const int hl = (r / p.tw) % p.th;
         const int nl = r / (p.tw * p.th);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        int tile_i = 0;
+        int tile_i = 0, epi_buf = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            mbar_wait(tmem_full_bar, tile_i & 1);
-            tc_fence_after();
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit, nullptr, nullptr, static_cast<int>(threadIdx.x) - 64);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit, nullptr, epi_buf,
+                                  nullptr, static_cast<int>(threadIdx.x) - 64);
             ++tile_i;
         }
     }

@@ -53,9 +53,55 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
+struct ResRegs {
+    uint4 h[4], l[4];
+};
+
+__device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Geometry of 64-channel output slice `s` of a tile for this thread: first channel of the slice (c0s), output pixel and
+// channel inside the output tensor (phase-fused transposed convs scatter slice -> output phase).
+struct SliceGeom {
+    int c0s, phs, cch;
+    long long opix;
+};
+__device__ __forceinline__ SliceGeom slice_geom(const ConvParams& p, const TileCoord& tc, int s, int h, int n, int y, int x, long long pix) {
+    SliceGeom g;
+    g.c0s = tc.nt0 + s * 64;
+    g.phs = 0;
+    g.cch = g.c0s + h * 32;
+    g.opix = pix;
+    if (p.fused_cout) {
+        g.phs = g.c0s / p.fused_cout;
+        g.cch -= g.phs * p.fused_cout;
+        g.opix = (static_cast<long long>(n) * p.OH + (2 * y + (g.phs >> 1))) * p.OW + (2 * x + (g.phs & 1));
+    }
+    return g;
+}
+__device__ __forceinline__ void load_residual(const ConvParams& p, const SliceGeom& g, bool valid, ResRegs& r) {
+    const bool on = p.res_hi != nullptr && valid && g.c0s < p.Cout;
+    const __half* r_hi = p.res_hi + g.opix * p.res_Ctot + g.cch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.h[i] = make_uint4(0, 0, 0, 0);
+        r.l[i] = make_uint4(0, 0, 0, 0);
+        if (on) {
+            r.h[i] = __ldg(reinterpret_cast<const uint4*>(r_hi + i * 8));
+            if (p.res_plane) r.l[i] = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + i * 8));
+        }
+    }
+}
+
+// `epi_buf` (in/out): staging buffer the next TMA-stored slice uses (rotates over p.epi_bufs buffers: buffer 0 sits after
+// the operand stages, buffers 1.. are carved from the top operand stages a short-K layer does not use, engine.cu).
 template <int BN, int NP>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_empty_bar,
-                                              const TileCoord& tc, int hl, int wl, int nl, int n_limit, uint8_t* stage,
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_full_bar,
+                                              uint32_t full_parity, uint64_t* tmem_empty_bar, const TileCoord& tc, int hl, int wl,
+                                              int nl, int n_limit, uint8_t* stage0, int& epi_buf,
                                               const CUtensorMap* const* omaps, int etid) {
     using Cfg = ConvCfg<BN, NP>;
     constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns handled per pass (all threads)
@@ -71,6 +117,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     const long long pix = (static_cast<long long>(n) * p.OH + oy) * p.OW + ox;
     const bool tstore = BN >= 64 && p.tma_store && !splitk && p.act != ACT_HEADS;
     const bool nacc3 = Cfg::NACC == 3 && !p.single_acc, nacc2 = Cfg::NACC >= 2 && !p.single_acc;
+    const float slope = p.act == ACT_LRELU ? 0.3f : (p.act == ACT_RELU ? 0.f : 1.f);  // act(v) = max(v, slope * v)
+    const int nbuf = p.epi_bufs;
+
+    // the first slice's residual is requested before the accumulators are even complete
+    ResRegs rcur;
+    if (BN >= 64) load_residual(p, slice_geom(p, tc, 0, h, n, y, x, pix), valid && !splitk, rcur);
+    if (p.dbg & 8) {
+        while (!mbar_try_wait(tmem_full_bar, full_parity)) __nanosleep(256);
+    } else {
+        mbar_wait(tmem_full_bar, full_parity);
+    }
+    tc_fence_after();
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass) {
         __syncwarp();  // lanes may arrive diverged (per-lane paths of the previous tile); tcgen05.ld is .aligned
@@ -138,81 +196,82 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         }
 #pragma unroll
         for (int sl = 0; sl < NSL; ++sl) {
-            const int c0s = tc.nt0 + pass * NCOL + sl * 64;  // first channel of the 64-wide slice
-            const int c0 = c0s + h * 32;                     // first of this thread's 32 channels
+            const int s = pass * NSL + sl;
+            const SliceGeom g = slice_geom(p, tc, s, h, n, y, x, pix);
+            const int c0 = g.c0s + h * 32;  // first of this thread's 32 accumulator columns
             if (splitk) {
                 if (valid) {
                     float4* dst = reinterpret_cast<float4*>(p.out_partial + z * p.partial_stride + pix * p.Cout_pad + c0);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        dst[g] = make_float4(acc[sl * 32 + 4 * g], acc[sl * 32 + 4 * g + 1], acc[sl * 32 + 4 * g + 2], acc[sl * 32 + 4 * g + 3]);
+                    for (int q = 0; q < 8; ++q)
+                        dst[q] = make_float4(acc[sl * 32 + 4 * q], acc[sl * 32 + 4 * q + 1], acc[sl * 32 + 4 * q + 2], acc[sl * 32 + 4 * q + 3]);
                 }
                 continue;
             }
-            if (c0s >= p.Cout) continue;  // uniform over the CTA
-            int phs = 0, cch = c0;
-            long long opix = pix;
-            if (p.fused_cout) {
-                phs = c0s / p.fused_cout;
-                cch = c0 - phs * p.fused_cout;
-                opix = (static_cast<long long>(n) * p.OH + (2 * y + (phs >> 1))) * p.OW + (2 * x + (phs & 1));
-            }
-            const __half* r_hi = (p.res_hi && valid) ? p.res_hi + opix * p.res_Ctot + cch : nullptr;
-            __half* o_hi = p.out_hi + opix * p.Ctot + p.c_off + cch;
+            // request the next slice's residual now; it lands while this slice is computed and staged
+            ResRegs rnext;
+            if (s + 1 < NPASS * NSL) load_residual(p, slice_geom(p, tc, s + 1, h, n, y, x, pix), valid, rnext);
+            else rnext = rcur;
+            if (g.c0s >= p.Cout) { rcur = rnext; continue; }  // uniform over the CTA
+            __half* o_hi = p.out_hi + g.opix * p.Ctot + p.c_off + g.cch;
             const int r = (nl * p.th + hl) * p.tw + wl;  // MMA row == row of the staging box
-            if (tstore) {
-                if (etid == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
+            uint8_t* stage = stage0 - epi_buf * Cfg::EPI_BYTES;
+            if (tstore && nbuf == 1) {
+                if (etid == 0) bulk_wait_read<0>();  // the previous TMA store has finished reading the only staging tile
                 named_bar_sync(1, kEpiThreads);
             }
-            // residual and scale / shift loads first (independent), then the arithmetic
-            uint4 rh[4], rl[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                rh[g] = make_uint4(0, 0, 0, 0); rl[g] = make_uint4(0, 0, 0, 0);
-                if (r_hi) {
-                    rh[g] = __ldg(reinterpret_cast<const uint4*>(r_hi + g * 8));
-                    if (p.res_plane) rl[g] = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + g * 8));
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int q = 0; q < 4; ++q) {
                 float sc8[8], sh8[8];
-                *reinterpret_cast<float4*>(sc8) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8));
-                *reinterpret_cast<float4*>(sc8 + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8 + 4));
-                *reinterpret_cast<float4*>(sh8) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8));
-                *reinterpret_cast<float4*>(sh8 + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8 + 4));
-                const __half* rhh = reinterpret_cast<const __half*>(&rh[g]);
-                const __half* rlh = reinterpret_cast<const __half*>(&rl[g]);
-                uint4 oh, ol;
-                __half* ohh = reinterpret_cast<__half*>(&oh);
-                __half* olh = reinterpret_cast<__half*>(&ol);
+                *reinterpret_cast<float4*>(sc8) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8));
+                *reinterpret_cast<float4*>(sc8 + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8 + 4));
+                *reinterpret_cast<float4*>(sh8) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8));
+                *reinterpret_cast<float4*>(sh8 + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8 + 4));
+                const uint32_t rh[4] = {rcur.h[q].x, rcur.h[q].y, rcur.h[q].z, rcur.h[q].w};
+                const uint32_t rl[4] = {rcur.l[q].x, rcur.l[q].y, rcur.l[q].z, rcur.l[q].w};
+                uint32_t oh[4], ol[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float val = acc[sl * 32 + g * 8 + j] * sc8[j] + sh8[j];
-                    if (r_hi) val += __half2float(rhh[j]) + __half2float(rlh[j]);
-                    val = act_apply(val, p.act);
-                    const __half hv = __float2half_rn(val);
-                    ohh[j] = hv;
-                    olh[j] = __float2half_rn(val - __half2float(hv));
+                for (int j = 0; j < 4; ++j) {
+                    float v0 = acc[sl * 32 + q * 8 + 2 * j] * sc8[2 * j] + sh8[2 * j];
+                    float v1 = acc[sl * 32 + q * 8 + 2 * j + 1] * sc8[2 * j + 1] + sh8[2 * j + 1];
+                    if (p.res_hi) {
+                        const float2 a = h2_to_f2(rh[j]), b = h2_to_f2(rl[j]);
+                        v0 += a.x + b.x;
+                        v1 += a.y + b.y;
+                    }
+                    v0 = fmaxf(v0, slope * v0);
+                    v1 = fmaxf(v1, slope * v1);
+                    oh[j] = f2_to_h2(v0, v1);
+                    const float2 back = h2_to_f2(oh[j]);
+                    ol[j] = f2_to_h2(v0 - back.x, v1 - back.y);
                 }
+                const uint4 ohv = make_uint4(oh[0], oh[1], oh[2], oh[3]), olv = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 if (tstore) {
-                    const uint32_t c16 = static_cast<uint32_t>(h * 4 + g);  // 16-byte chunk inside the 128-byte row
+                    const uint32_t c16 = static_cast<uint32_t>(h * 4 + q);  // 16-byte chunk inside the 128-byte row
                     const uint32_t off = static_cast<uint32_t>(r) * 128 + ((c16 ^ (static_cast<uint32_t>(r) & 7u)) << 4);
-                    *reinterpret_cast<uint4*>(stage + off) = oh;
-                    if (NP == 2) *reinterpret_cast<uint4*>(stage + 128 * 128 + off) = ol;
+                    *reinterpret_cast<uint4*>(stage + off) = ohv;
+                    if (NP == 2) *reinterpret_cast<uint4*>(stage + 128 * 128 + off) = olv;
                 } else if (valid) {
-                    *reinterpret_cast<uint4*>(o_hi + g * 8) = oh;
-                    if (p.out_plane) *reinterpret_cast<uint4*>(o_hi + p.out_plane + g * 8) = ol;
+                    *reinterpret_cast<uint4*>(o_hi + q * 8) = ohv;
+                    if (p.out_plane) *reinterpret_cast<uint4*>(o_hi + p.out_plane + q * 8) = olv;
                 }
             }
             if (tstore) {
                 fence_proxy_async();
+                // with >= 2 staging tiles one barrier per slice is enough: before it, the issuing thread makes sure the
+                // store that last used the NEXT slice's tile has finished reading it
+                if (etid == 0) {
+                    if (nbuf == 2) bulk_wait_read<0>();
+                    else if (nbuf == 3) bulk_wait_read<1>();
+                }
                 named_bar_sync(1, kEpiThreads);
                 if (etid == 0) {
-                    tma_store_5d(omaps[p.sy == 2 ? (p.fused_cout ? phs : z) : 0], stage, p.c_off + (cch - h * 32), tc.x0, tc.y0, tc.n0, 0);
+                    tma_store_5d(omaps[p.sy == 2 ? (p.fused_cout ? g.phs : z) : 0], stage, p.c_off + (g.cch - h * 32), tc.x0, tc.y0, tc.n0, 0);
                     bulk_commit_group();
                 }
+                epi_buf = epi_buf + 1 == nbuf ? 0 : epi_buf + 1;
             }
+            rcur = rnext;
         }
     }
 }
@@ -263,72 +322,88 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int nst = (p.dbg >> 8) > 0 && (p.dbg >> 8) < STAGES ? (p.dbg >> 8) : STAGES;
+    const int nst = p.nst > 0 && p.nst < STAGES ? p.nst : STAGES;  // short-K layers give their top stages to the epilogue
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int itg = 0;
+            int st = 0;
+            uint32_t ph = 0;  // running stage / phase (no per-iteration division: the stage count is a run-time value)
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, t, n_limit);
                 if (!tc.live) continue;
-                for (int it = 0; it < tc.nk; ++it, ++itg) {
-                    const int s = itg % nst;
-                    const uint32_t ph = (itg / nst) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    const int4 k = __ldg(&p.kit[tc.kbeg + it]);
-                    uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+                int4 k = __ldg(&p.kit[tc.kbeg]);
+                for (int it = 0; it < tc.nk; ++it) {
+                    const int4 kn = __ldg(&p.kit[tc.kbeg + (it + 1 < tc.nk ? it + 1 : it)]);  // next entry, in flight during the wait
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    uint8_t* sA = smem + st * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + Cfg::A_BYTES;
                     const uint32_t tx = ((p.dbg & 1) ? 0 : Cfg::A_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
-                    if (tx == 0) { mbar_arrive(&full_bar[s]); continue; }
-                    mbar_arrive_expect_tx(&full_bar[s], tx);
-                    const int mi = k.x & 0xff;
-                    const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
-                    if (!(p.dbg & 1)) tma_load_5d(mA, &full_bar[s], sA, k.w, tc.x0 + k.z, tc.y0 + k.y, tc.n0, 0);
-                    if (!(p.dbg & 2)) tma_load_4d(&mB, &full_bar[s], sB, 0, tc.nt0, 0, tc.kbeg + it);
+                    if (tx == 0) {
+                        mbar_arrive(&full_bar[st]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[st], tx);
+                        const int mi = k.x & 0xff;
+                        const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
+                        if (!(p.dbg & 1)) tma_load_5d(mA, &full_bar[st], sA, k.w, tc.x0 + k.z, tc.y0 + k.y, tc.n0, 0);
+                        if (!(p.dbg & 2)) tma_load_4d(&mB, &full_bar[st], sB, 0, tc.nt0, 0, tc.kbeg + it);
+                    }
+                    k = kn;
+                    if (++st == nst) { st = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, BN < 16 ? 16 : BN);
-            int itg = 0, tile_i = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const TileCoord tc = decode_tile<BN>(p, t, n_limit);
-                if (!tc.live) continue;
-                mbar_wait(tmem_empty_bar, (tile_i & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
+        // The WHOLE warp runs this loop convergently and only the tcgen05 instructions sit under elect_one(): every
+        // operand of tcgen05.mma must live in uniform registers, and inside an `if (lane == 0)` region the compiler keeps
+        // the loop state in per-thread registers and wraps each MMA in R2UR moves plus an ELECT / BRA.U.ANY loop -- about
+        // as long as the MMA itself runs, i.e. the kernel was issue-bound (98 instead of 75 cycles per MMA).  For the
+        // same reason the per-iteration k16-step counts come from the kernel parameters (constant bank -> uniform
+        // registers), not from global memory.
+        constexpr uint32_t idesc = umma_idesc_f16(128, BN < 16 ? 16 : BN);
+        const bool one_acc = p.single_acc != 0;
+        const uint32_t cross = one_acc ? 0u : (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
+        const bool split_hh = Cfg::NACC == 3 && !one_acc;
+        const uint32_t smem_a0 = smem_u32(smem);
+        int st = 0, tile_i = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const TileCoord tc = decode_tile<BN>(p, t, n_limit);
+            if (!tc.live) continue;
+            mbar_wait(tmem_empty_bar, (tile_i & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
+            int g = 0;
+            for (int it = 0; it < tc.nk; ++it) {
+                const int ksteps = p.ksteps_tab[tc.kbeg + it];
+                mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
-                int g = 0;
-                for (int it = 0; it < tc.nk; ++it, ++itg) {
-                    const int s = itg % nst;
-                    const uint32_t ph = (itg / nst) & 1;
-                    const int ksteps = __ldg(&p.kit[tc.kbeg + it].x) >> 8;
-                    if (!(p.dbg & 4)) mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t aA = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    const uint32_t aB = aA + Cfg::A_BYTES;
+                const uint32_t aA = smem_a0 + st * Cfg::STAGE_BYTES;
+                const uint32_t aB = aA + Cfg::A_BYTES;
 #pragma unroll 1
-                    for (int kk = 0; kk < ksteps; ++kk, ++g) {
-                        const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
-                        const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                        if (NP == 2) {
-                            const uint32_t cross = p.single_acc ? 0u : (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
-                            if (Cfg::NACC == 3 && !p.single_acc) umma_f16(tmem_base + (g & 1) * Cfg::ACC_STRIDE, a_hi, b_hi, idesc, g >= 2 ? 1u : 0u);
-                            else umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
-                            const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
-                            const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, (g > 0 || p.single_acc) ? 1u : 0u);
+                for (int kk = 0; kk < ksteps; ++kk, ++g) {
+                    const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
+                    const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
+                    if (NP == 2) {
+                        const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
+                        const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
+                        const uint32_t d_hh = split_hh ? tmem_base + (g & 1) * Cfg::ACC_STRIDE : tmem_base;
+                        const uint32_t acc_hh = split_hh ? (g >= 2 ? 1u : 0u) : (g > 0 ? 1u : 0u);
+                        const uint32_t acc_x = (g > 0 || one_acc) ? 1u : 0u;
+                        if (elect_one()) {
+                            umma_f16(d_hh, a_hi, b_hi, idesc, acc_hh);
+                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, acc_x);
                             umma_f16(tmem_base + cross, a_hi, b_lo, idesc, 1u);
-                        } else {
-                            umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                         }
+                    } else {
+                        if (elect_one()) umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(tmem_full_bar);
-                ++tile_i;
+                if (elect_one()) umma_commit(&empty_bar[st]);
+                if (++st == nst) { st = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(tmem_full_bar);
+            ++tile_i;
         }
+        __syncwarp();
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;
@@ -338,14 +413,12 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         const int nl = r / (p.tw * p.th);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const CUtensorMap* const omaps[4] = {&mO0, &mO1, &mO2, &mO3};
-        int tile_i = 0;
+        int tile_i = 0, epi_buf = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            mbar_wait(tmem_full_bar, tile_i & 1);
-            tc_fence_after();
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_empty_bar, tc, hl, wl, nl, n_limit, BN >= 64 ? sEpi : nullptr, omaps,
-                                  static_cast<int>(threadIdx.x) - 64);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit,
+                                  BN >= 64 ? sEpi : nullptr, epi_buf, omaps, static_cast<int>(threadIdx.x) - 64);
             ++tile_i;
         }
         if (threadIdx.x == 64) bulk_wait_all();  // outstanding TMA stores complete before the CTA retires

@@ -427,7 +427,8 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     if (const char* e = getenv("P2P_HALO")) use_halo = atoi(e) != 0;
     if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
     if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
-    if (const char* e = getenv("P2P_KROT")) krot = atoi(e) != 0;
+    if (const char* e = getenv("P2P_EPI_NK")) epi_nk = atoi(e);
+    if (const char* e = getenv("P2P_PROF_LAYERS")) prof_layers = atoi(e) != 0;
 
     tensors.resize(plan.tensors.size());
     for (size_t i = 0; i < plan.tensors.size(); ++i) {
@@ -775,7 +776,9 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 p.res_Ctot = plan.tensors[c.res_tensor].C;
             }
             p.n_active = n_active;
-            p.krot = 0;
+            P2P_CHECK(c.kit.size() <= sizeof(p.ksteps_tab), "conv %s: %zu k-iterations exceed the parameter table", c.name.c_str(), c.kit.size());
+            for (size_t i = 0; i < c.kit.size(); ++i) p.ksteps_tab[i] = static_cast<uint8_t>(c.kit[i].x >> 8);
+            int max_nk = 0;          // most k-iterations any tile of this launch runs
             {
                 int max_steps = 0;   // longest accumulation chain of this launch, in k16 steps
                 const int nz = c.splitk > 1 ? 1 : c.phases;
@@ -784,6 +787,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     const int kb = c.kstart[z], ke = c.splitk > 1 ? std::min<int>(c.splitk_chunk, static_cast<int>(c.kit.size())) : c.kstart[z + 1];
                     for (int it = kb; it < ke; ++it) steps += c.kit[it].x >> 8;
                     max_steps = std::max(max_steps, steps);
+                    max_nk = std::max(max_nk, ke - kb);
                 }
                 p.single_acc = (persistent && np == 2 && max_steps <= single_acc_steps) ? 1 : 0;
             }
@@ -819,6 +823,18 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 }
             } else if (persistent) {
                 p.tma_store = (tma_store && rt.has_out) ? 1 : 0;
+                {
+                    // epilogue-bound layers (few k-iterations per tile) run on fewer operand stages and use the freed
+                    // shared memory as extra output staging tiles, so TMA stores overlap the next slice's arithmetic
+                    const int stage_bytes = np * 128 * 128 + np * c.BN * 128, epi_bytes = np * 128 * 128;
+                    const int stages = std::min(6, 200 * 1024 / stage_bytes);
+                    int nst = stages;
+                    if (max_nk <= epi_nk && stages > 2) nst = 2;
+                    else if (c.BN == 64 && stages > 3) nst = stages - 1;
+                    p.nst = nst;
+                    p.epi_bufs = (p.tma_store && c.BN >= 64) ? std::min(3, 1 + (stages - nst) * stage_bytes / epi_bytes) : 1;
+                    if (const char* e = getenv("P2P_NST")) { p.nst = atoi(e); p.epi_bufs = 1; }
+                }
                 const int ctas = std::min<long long>(static_cast<long long>(grid.x) * grid.y * grid.z, num_sms);
                 if (c.BN == 256) {
                     if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
@@ -862,7 +878,9 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             P2P_CUDA(cudaEventElapsedTime(&ms, pev[i - 1], pev[i]));
             prof[pkind[i]] += ms;
             prof[2 + pkind[i]] += 1;
+            if (prof_layers) fprintf(stderr, "%zu:%.0f ", i - 1, ms * 1000.f);  // per-launch microseconds (P2P_PROF_LAYERS=1)
         }
+        if (prof_layers) fprintf(stderr, "\n");
         for (auto e : pev) cudaEventDestroy(e);
     }
 }
