@@ -61,6 +61,7 @@ struct ConvParams {
                      // (the per-lane 16-byte stores of a row-per-thread epilogue are uncoalesced: 32 lines per instruction)
     int single_acc;  // short K loops (<= 40 k16 steps): one TMEM accumulator instead of three (the round-toward-zero bias the
                      // split guards against grows with the chain length; the epilogue drain is 3x cheaper)
+    int res_tma;     // persistent kernel: the residual arrives by TMA (tensor map mR) in two shared-memory tiles, two slices ahead
     int nst;         // persistent kernel: operand stages to use (0 = all).  Short-K layers run on fewer stages and hand the
     int epi_bufs;    // top ones to the epilogue as extra output staging tiles (epi_bufs = 1..3 tiles of EPI_BYTES)
     int dbg;         // bottleneck experiments on the persistent kernel (WRONG RESULTS): bit0 skip A loads, bit1 skip B loads,
@@ -83,7 +84,8 @@ struct ConvCfg {
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
     static constexpr int EPI_BYTES = NP * 128 * 128;  // output staging for the TMA-store epilogue (persistent kernel)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int SMEM_BYTES_P = SMEM_BYTES + (BN >= 64 ? EPI_BYTES : 0);
+    static constexpr int CONST_BYTES = (BN >= 64 && BN <= 128) ? 2 * BN * 4 : 0;  // folded BN scale / shift of a tile column
+    static constexpr int SMEM_BYTES_P = SMEM_BYTES + (BN >= 64 ? EPI_BYTES : 0) + CONST_BYTES;
     // fp16x3 keeps THREE accumulators in TMEM: two for the hi*hi products (even / odd k-steps) and one
     // for the 2^-11-times-smaller cross terms.  The tensor core rounds the fp32 accumulator toward zero
     // after every MMA; splitting the chains divides that bias (measured: resnet50 decode max error

@@ -28,7 +28,7 @@ struct HaloCfg {
     static constexpr int B_BYTES = NP * BN * 128;
     static constexpr int B_ROOM = 208 * 1024 - SLAB_BUFS * SLAB_BYTES;
     static constexpr int B_STAGES = B_ROOM / B_BYTES > 8 ? 8 : B_ROOM / B_BYTES;
-    static constexpr int SMEM_BYTES = SLAB_BUFS * SLAB_BYTES + B_STAGES * B_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = SLAB_BUFS * SLAB_BYTES + B_STAGES * B_BYTES + 1024 + 256 + 2048;  // + scale / shift staging
 };
 
 // slab table entry (p.kit): {map index | (k16 steps << 8), c0, first packed-weight k-iteration of (source, tap 0, chunk), chunks of the source}
@@ -171,12 +171,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
         const int hl = (r / p.tw) % p.th;
         const int nl = r / (p.tw * p.th);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        int tile_i = 0, epi_buf = 0;
+        EpiState e;
+        e.stage0 = nullptr; e.res0 = nullptr; e.res_bar = nullptr;
+        e.s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~static_cast<uintptr_t>(15));
+        e.s_shift = e.s_scale + BN;
+        e.epi_buf = 0; e.cur_nt0 = -1; e.res_cnt = 0;
+        int tile_i = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit, nullptr, epi_buf,
-                                  nullptr, static_cast<int>(threadIdx.x) - 64);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit, e, nullptr, nullptr,
+                                  nullptr, nullptr, static_cast<int>(threadIdx.x) - 64);
             ++tile_i;
         }
     }

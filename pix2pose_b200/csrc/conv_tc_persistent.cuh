@@ -53,10 +53,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
-struct ResRegs {
-    uint4 h[4], l[4];
-};
-
 __device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 __device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -82,32 +78,34 @@ __device__ __forceinline__ SliceGeom slice_geom(const ConvParams& p, const TileC
     }
     return g;
 }
-__device__ __forceinline__ void load_residual(const ConvParams& p, const SliceGeom& g, bool valid, ResRegs& r) {
-    const bool on = p.res_hi != nullptr && valid && g.c0s < p.Cout;
-    const __half* r_hi = p.res_hi + g.opix * p.res_Ctot + g.cch;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        r.h[i] = make_uint4(0, 0, 0, 0);
-        r.l[i] = make_uint4(0, 0, 0, 0);
-        if (on) {
-            r.h[i] = __ldg(reinterpret_cast<const uint4*>(r_hi + i * 8));
-            if (p.res_plane) r.l[i] = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + i * 8));
-        }
-    }
-}
 
-// `epi_buf` (in/out): staging buffer the next TMA-stored slice uses (rotates over p.epi_bufs buffers: buffer 0 sits after
-// the operand stages, buffers 1.. are carved from the top operand stages a short-K layer does not use, engine.cu).
+// Shared-memory resources and running state of the epilogue warps (all values are uniform over the 256 threads).
+//   stage0     output staging tile 0 (tiles 1.. lie EPI_BYTES below each other, in operand stages the layer does not use)
+//   res0       residual tiles (p.res_tma): two tiles of EPI_BYTES; the TMA producer warp fills tile (j & 1) with slice j's
+//              residual as soon as slice j - 2 has released it (res_bar[0..1] = full, res_bar[2..3] = empty)
+//   s_scale/s_shift  folded BN scale / shift of the current tile column (BN <= 128)
+struct EpiState {
+    uint8_t* stage0;
+    uint8_t* res0;
+    uint64_t* res_bar;
+    float* s_scale;
+    float* s_shift;
+    int epi_buf;      // staging tile the next stored slice uses
+    int cur_nt0;      // tile column whose scale / shift are in shared memory
+    uint32_t res_cnt; // residual slices consumed so far (buffer = cnt & 1, parity = (cnt >> 1) & 1)
+};
+
 template <int BN, int NP>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_full_bar,
                                               uint32_t full_parity, uint64_t* tmem_empty_bar, const TileCoord& tc, int hl, int wl,
-                                              int nl, int n_limit, uint8_t* stage0, int& epi_buf,
-                                              const CUtensorMap* const* omaps, int etid) {
+                                              int nl, int n_limit, EpiState& e, const CUtensorMap* mO0, const CUtensorMap* mO1,
+                                              const CUtensorMap* mO2, const CUtensorMap* mO3, int etid) {
     using Cfg = ConvCfg<BN, NP>;
     constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns handled per pass (all threads)
     constexpr int NPASS = BN > 128 ? BN / 128 : 1;
     constexpr int NSL = NCOL >= 64 ? NCOL / 64 : 1;               // 64-channel slices per pass
     constexpr int MYC = BN >= 64 ? 32 * NSL : NCOL;               // columns this thread owns per pass
+    constexpr bool SMEM_CONST = BN >= 64 && BN <= 128;            // scale / shift of the tile column staged in shared memory
     const int h = etid >> 7;                                     // column group
     const bool splitk = p.splitk_chunk > 0;
     const int z = tc.z, zi = splitk ? 0 : z;
@@ -119,15 +117,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     const bool nacc3 = Cfg::NACC == 3 && !p.single_acc, nacc2 = Cfg::NACC >= 2 && !p.single_acc;
     const float slope = p.act == ACT_LRELU ? 0.3f : (p.act == ACT_RELU ? 0.f : 1.f);  // act(v) = max(v, slope * v)
     const int nbuf = p.epi_bufs;
+    const bool res_tma = BN >= 64 && p.res_tma != 0;
+    const bool res_ldg = BN >= 64 && !res_tma && p.res_hi != nullptr && !splitk;
 
-    // the first slice's residual is requested before the accumulators are even complete
-    ResRegs rcur;
-    if (BN >= 64) load_residual(p, slice_geom(p, tc, 0, h, n, y, x, pix), valid && !splitk, rcur);
-    if (p.dbg & 8) {
-        while (!mbar_try_wait(tmem_full_bar, full_parity)) __nanosleep(256);
-    } else {
-        mbar_wait(tmem_full_bar, full_parity);
+    if (SMEM_CONST && !splitk && tc.nt0 != e.cur_nt0) {
+        // new tile column (at most grid_n * grid_z times per CTA): restage its folded BN constants
+        named_bar_sync(1, kEpiThreads);
+        if (etid < BN) {
+            e.s_scale[etid] = __ldg(p.scale + tc.nt0 + etid);
+            e.s_shift[etid] = __ldg(p.shift + tc.nt0 + etid);
+        }
+        named_bar_sync(1, kEpiThreads);
+        e.cur_nt0 = tc.nt0;
     }
+    mbar_wait(tmem_full_bar, full_parity);
     tc_fence_after();
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass) {
@@ -188,8 +191,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         d[c] = tanhf(acc[ph * 4 + c] * __ldg(&p.scale[ph * 4 + c]) + __ldg(&p.shift[ph * 4 + c]));
-                    const float e = acc[ph * 4 + 3] * __ldg(&p.scale[ph * 4 + 3]) + __ldg(&p.shift[ph * 4 + 3]);
-                    p.out_prob[opix] = 1.f / (1.f + expf(-e));
+                    const float ev = acc[ph * 4 + 3] * __ldg(&p.scale[ph * 4 + 3]) + __ldg(&p.shift[ph * 4 + 3]);
+                    p.out_prob[opix] = 1.f / (1.f + expf(-ev));
                 }
             }
             continue;
@@ -208,33 +211,50 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 }
                 continue;
             }
-            // request the next slice's residual now; it lands while this slice is computed and staged
-            ResRegs rnext;
-            if (s + 1 < NPASS * NSL) load_residual(p, slice_geom(p, tc, s + 1, h, n, y, x, pix), valid, rnext);
-            else rnext = rcur;
-            if (g.c0s >= p.Cout) { rcur = rnext; continue; }  // uniform over the CTA
+            if (g.c0s >= p.Cout) continue;  // uniform over the CTA (never with res_tma: Cout is a multiple of BN there)
             __half* o_hi = p.out_hi + g.opix * p.Ctot + p.c_off + g.cch;
-            const int r = (nl * p.th + hl) * p.tw + wl;  // MMA row == row of the staging box
-            uint8_t* stage = stage0 - epi_buf * Cfg::EPI_BYTES;
+            const __half* r_hi = p.res_hi + g.opix * p.res_Ctot + g.cch;
+            const int r = (nl * p.th + hl) * p.tw + wl;  // MMA row == row of the staging / residual box
+            uint8_t* stage = e.stage0 - e.epi_buf * Cfg::EPI_BYTES;
+            const uint8_t* rbuf = e.res0 - (e.res_cnt & 1u) * Cfg::EPI_BYTES;
+            if (res_tma) mbar_wait(&e.res_bar[e.res_cnt & 1u], (e.res_cnt >> 1) & 1u);  // this slice's residual has landed
             if (tstore && nbuf == 1) {
                 if (etid == 0) bulk_wait_read<0>();  // the previous TMA store has finished reading the only staging tile
                 named_bar_sync(1, kEpiThreads);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+                const uint32_t c16 = static_cast<uint32_t>(h * 4 + q);  // 16-byte chunk inside the 128-byte row
+                const uint32_t off = static_cast<uint32_t>(r) * 128 + ((c16 ^ (static_cast<uint32_t>(r) & 7u)) << 4);
                 float sc8[8], sh8[8];
-                *reinterpret_cast<float4*>(sc8) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8));
-                *reinterpret_cast<float4*>(sc8 + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8 + 4));
-                *reinterpret_cast<float4*>(sh8) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8));
-                *reinterpret_cast<float4*>(sh8 + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8 + 4));
-                const uint32_t rh[4] = {rcur.h[q].x, rcur.h[q].y, rcur.h[q].z, rcur.h[q].w};
-                const uint32_t rl[4] = {rcur.l[q].x, rcur.l[q].y, rcur.l[q].z, rcur.l[q].w};
+                if (SMEM_CONST) {
+                    const int cl = s * 64 + h * 32 + q * 8;  // column inside the tile
+                    *reinterpret_cast<float4*>(sc8) = *reinterpret_cast<const float4*>(e.s_scale + cl);
+                    *reinterpret_cast<float4*>(sc8 + 4) = *reinterpret_cast<const float4*>(e.s_scale + cl + 4);
+                    *reinterpret_cast<float4*>(sh8) = *reinterpret_cast<const float4*>(e.s_shift + cl);
+                    *reinterpret_cast<float4*>(sh8 + 4) = *reinterpret_cast<const float4*>(e.s_shift + cl + 4);
+                } else {
+                    *reinterpret_cast<float4*>(sc8) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8));
+                    *reinterpret_cast<float4*>(sc8 + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + q * 8 + 4));
+                    *reinterpret_cast<float4*>(sh8) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8));
+                    *reinterpret_cast<float4*>(sh8 + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + q * 8 + 4));
+                }
+                uint4 rhv = make_uint4(0, 0, 0, 0), rlv = make_uint4(0, 0, 0, 0);
+                if (res_tma) {
+                    rhv = *reinterpret_cast<const uint4*>(rbuf + off);
+                    if (NP == 2) rlv = *reinterpret_cast<const uint4*>(rbuf + 128 * 128 + off);
+                } else if (res_ldg && valid) {
+                    rhv = __ldg(reinterpret_cast<const uint4*>(r_hi + q * 8));
+                    if (p.res_plane) rlv = __ldg(reinterpret_cast<const uint4*>(r_hi + p.res_plane + q * 8));
+                }
+                const uint32_t rh[4] = {rhv.x, rhv.y, rhv.z, rhv.w};
+                const uint32_t rl[4] = {rlv.x, rlv.y, rlv.z, rlv.w};
                 uint32_t oh[4], ol[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float v0 = acc[sl * 32 + q * 8 + 2 * j] * sc8[2 * j] + sh8[2 * j];
                     float v1 = acc[sl * 32 + q * 8 + 2 * j + 1] * sc8[2 * j + 1] + sh8[2 * j + 1];
-                    if (p.res_hi) {
+                    if (res_tma || res_ldg) {
                         const float2 a = h2_to_f2(rh[j]), b = h2_to_f2(rl[j]);
                         v0 += a.x + b.x;
                         v1 += a.y + b.y;
@@ -247,8 +267,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 }
                 const uint4 ohv = make_uint4(oh[0], oh[1], oh[2], oh[3]), olv = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 if (tstore) {
-                    const uint32_t c16 = static_cast<uint32_t>(h * 4 + q);  // 16-byte chunk inside the 128-byte row
-                    const uint32_t off = static_cast<uint32_t>(r) * 128 + ((c16 ^ (static_cast<uint32_t>(r) & 7u)) << 4);
                     *reinterpret_cast<uint4*>(stage + off) = ohv;
                     if (NP == 2) *reinterpret_cast<uint4*>(stage + 128 * 128 + off) = olv;
                 } else if (valid) {
@@ -266,12 +284,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 }
                 named_bar_sync(1, kEpiThreads);
                 if (etid == 0) {
-                    tma_store_5d(omaps[p.sy == 2 ? (p.fused_cout ? g.phs : z) : 0], stage, p.c_off + (g.cch - h * 32), tc.x0, tc.y0, tc.n0, 0);
+                    const CUtensorMap* mo = mO0;
+                    if (p.sy == 2) {
+                        const int mi = p.fused_cout ? g.phs : z;
+                        mo = mi == 0 ? mO0 : (mi == 1 ? mO1 : (mi == 2 ? mO2 : mO3));
+                    }
+                    tma_store_5d(mo, stage, p.c_off + (g.cch - h * 32), tc.x0, tc.y0, tc.n0, 0);
                     bulk_commit_group();
                 }
-                epi_buf = epi_buf + 1 == nbuf ? 0 : epi_buf + 1;
+                e.epi_buf = e.epi_buf + 1 == nbuf ? 0 : e.epi_buf + 1;
+            } else if (res_tma) {
+                named_bar_sync(1, kEpiThreads);  // everyone is done with the residual tile
             }
-            rcur = rnext;
+            if (res_tma) {
+                if (etid == 0) mbar_arrive(&e.res_bar[2 + (e.res_cnt & 1u)]);  // tile released: the producer refills it (slice + 2)
+                ++e.res_cnt;
+            }
         }
     }
 }
@@ -282,7 +310,8 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                           const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                           const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO0,
                           const __grid_constant__ CUtensorMap mO1, const __grid_constant__ CUtensorMap mO2,
-                          const __grid_constant__ CUtensorMap mO3, const __grid_constant__ ConvParams p) {
+                          const __grid_constant__ CUtensorMap mO3, const __grid_constant__ CUtensorMap mR,
+                          const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN, NP>;
     constexpr int STAGES = Cfg::STAGES;
     const int warp = threadIdx.x >> 5;
@@ -302,7 +331,9 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+    uint64_t* res_bar = tmem_empty_bar + 1;  // residual tiles (p.res_tma): [0..1] full, [2..3] empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [BN] + [BN] (BN <= 128, Cfg::CONST_BYTES)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mA0);
@@ -313,6 +344,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(tmem_empty_bar, kEpiWarps);  // one arrival per epilogue warp
+        for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     } else if (warp == 2) {
         tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -324,34 +356,48 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
 
     const int nst = p.nst > 0 && p.nst < STAGES ? p.nst : STAGES;  // short-K layers give their top stages to the epilogue
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;  // running stage / phase (no per-iteration division: the stage count is a run-time value)
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const TileCoord tc = decode_tile<BN>(p, t, n_limit);
-                if (!tc.live) continue;
-                int4 k = __ldg(&p.kit[tc.kbeg]);
-                for (int it = 0; it < tc.nk; ++it) {
-                    const int4 kn = __ldg(&p.kit[tc.kbeg + (it + 1 < tc.nk ? it + 1 : it)]);  // next entry, in flight during the wait
-                    mbar_wait(&empty_bar[st], ph ^ 1);
-                    uint8_t* sA = smem + st * Cfg::STAGE_BYTES;
-                    uint8_t* sB = sA + Cfg::A_BYTES;
-                    const uint32_t tx = ((p.dbg & 1) ? 0 : Cfg::A_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
+        // ===================== TMA producer (whole warp convergent, TMA issue under elect_one; see the MMA issuer) =====================
+        int st = 0;
+        uint32_t ph = 0;  // running stage / phase (no per-iteration division: the stage count is a run-time value)
+        uint32_t res_j = 0;  // residual slices issued
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const TileCoord tc = decode_tile<BN>(p, t, n_limit);
+            if (!tc.live) continue;
+            int4 k = __ldg(&p.kit[tc.kbeg]);
+            for (int it = 0; it < tc.nk; ++it) {
+                const int4 kn = __ldg(&p.kit[tc.kbeg + (it + 1 < tc.nk ? it + 1 : it)]);  // next entry, in flight during the wait
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                uint8_t* sA = smem + st * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + Cfg::A_BYTES;
+                const uint32_t tx = ((p.dbg & 1) ? 0 : Cfg::A_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
+                const int mi = k.x & 0xff;
+                const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
+                if (elect_one()) {
                     if (tx == 0) {
                         mbar_arrive(&full_bar[st]);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[st], tx);
-                        const int mi = k.x & 0xff;
-                        const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
                         if (!(p.dbg & 1)) tma_load_5d(mA, &full_bar[st], sA, k.w, tc.x0 + k.z, tc.y0 + k.y, tc.n0, 0);
                         if (!(p.dbg & 2)) tma_load_4d(&mB, &full_bar[st], sB, 0, tc.nt0, 0, tc.kbeg + it);
                     }
-                    k = kn;
-                    if (++st == nst) { st = 0; ph ^= 1; }
+                }
+                k = kn;
+                if (++st == nst) { st = 0; ph ^= 1; }
+            }
+            if (BN >= 64 && p.res_tma) {
+                // this tile's residual, one 64-channel slice per shared-memory tile, as soon as the epilogue has released it
+#pragma unroll 1
+                for (int sl = 0; sl < BN / 64; ++sl, ++res_j) {
+                    const uint32_t b = res_j & 1u;
+                    mbar_wait(&res_bar[2 + b], ((res_j >> 1) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&res_bar[b], Cfg::EPI_BYTES);
+                        tma_load_5d(&mR, &res_bar[b], sEpi - (1 + b) * Cfg::EPI_BYTES, tc.nt0 + sl * 64, tc.x0, tc.y0, tc.n0, 0);
+                    }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // The WHOLE warp runs this loop convergently and only the tcgen05 instructions sit under elect_one(): every
@@ -412,13 +458,22 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         const int hl = (r / p.tw) % p.th;
         const int nl = r / (p.tw * p.th);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const CUtensorMap* const omaps[4] = {&mO0, &mO1, &mO2, &mO3};
-        int tile_i = 0, epi_buf = 0;
+        const int etid = static_cast<int>(threadIdx.x) - 64;
+        EpiState e;
+        e.stage0 = sEpi;
+        e.res0 = sEpi - Cfg::EPI_BYTES;  // residual tiles 0 / 1 below the staging tile (operand stages >= nst are unused)
+        e.res_bar = res_bar;
+        e.s_scale = s_scale;
+        e.s_shift = s_scale + BN;
+        e.epi_buf = 0;
+        e.cur_nt0 = -1;
+        e.res_cnt = 0;
+        int tile_i = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit,
-                                  BN >= 64 ? sEpi : nullptr, epi_buf, omaps, static_cast<int>(threadIdx.x) - 64);
+            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit, e, &mO0, &mO1,
+                                  &mO2, &mO3, etid);
             ++tile_i;
         }
         if (threadIdx.x == 64) bulk_wait_all();  // outstanding TMA stores complete before the CTA retires

@@ -194,7 +194,6 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
     c.Cout = 0;
     for (auto& w : c.parts) c.Cout += layer_cout(L[find_layer(L, w.layer)]);
     if (c.Cout < 64) { c.BN = 16; c.Cout_pad = 16; }
-    else if (c.Cout % 256 == 0 && getenv("P2P_BN256") && atoi(getenv("P2P_BN256"))) { c.BN = 256; c.Cout_pad = c.Cout; }
     else if (c.Cout % 128 == 0) { c.BN = 128; c.Cout_pad = c.Cout; }
     else { c.BN = 64; c.Cout_pad = (c.Cout + 63) / 64 * 64; }
 
@@ -314,6 +313,17 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         c.splitk_chunk = 16;
         c.splitk = static_cast<int>((c.kit.size() + c.splitk_chunk - 1) / c.splitk_chunk);
     }
+    {
+        // N = 256 tiles for wide layers with a long K loop: the tensor-pipe-bound convs are power / clock limited and an
+        // N = 256 MMA reads 25 % less shared memory per FLOP (measured: deconv2 1.77 -> 1.55 ms per 256 crops).  Short-K
+        // layers stay at 128: they are epilogue-bound and BN = 256 leaves no shared memory for staging tiles.
+        const char* e = getenv("P2P_BN256");
+        const int min_kit = e ? atoi(e) : 100;   // P2P_BN256=0 disables, otherwise = minimum k-iterations per tile
+        if (min_kit > 0 && c.BN == 128 && c.Cout % 256 == 0 && c.splitk <= 1 && c.phases == 1 && c.kind != K_CONVT_FUSED &&
+            static_cast<int>(c.kit.size()) >= min_kit) {
+            c.BN = 256; c.Cout_pad = c.Cout;
+        }
+    }
     if (c.phases == 1)
         for (int z = 1; z < 5; ++z) c.kstart[z] = c.kstart[1];
     c.tw = std::min(c.W, 16);
@@ -428,6 +438,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
     if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
     if (const char* e = getenv("P2P_EPI_NK")) epi_nk = atoi(e);
+    if (const char* e = getenv("P2P_RES_TMA")) res_tma = atoi(e) != 0;
     if (const char* e = getenv("P2P_PROF_LAYERS")) prof_layers = atoi(e) != 0;
 
     tensors.resize(plan.tensors.size());
@@ -506,6 +517,22 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 }
             }
             rt.has_out = true;
+        }
+        memset(&rt.mapRes, 0, sizeof(rt.mapRes));
+        rt.has_res = false;
+        if (rt.has_out && c.res_tensor >= 0 && c.sy == 1 && c.kind != K_DENSE && c.kind != K_CONVT_FUSED && c.Cout % c.BN == 0) {
+            // residual tensor viewed exactly like the output tensor: the producer warp fetches the (64 ch, tw, th, nb, plane)
+            // box of every output slice into shared memory
+            const TensorSpec& tr = plan.tensors[c.res_tensor];
+            const TensorSpec& to = plan.tensors[c.out_tensor];
+            if (tr.H == to.H && tr.W == to.W && tr.C >= c.Cout) {
+                const cuuint64_t RC = tr.C, RW = tr.W, RH = tr.H;
+                cuuint32_t box[5] = {64, (cuuint32_t)c.tw, (cuuint32_t)c.th, (cuuint32_t)c.nb, (cuuint32_t)np};
+                cuuint64_t dims[5] = {RC, RW, RH, (cuuint64_t)cap, (cuuint64_t)np};
+                cuuint64_t str[4] = {RC * 2, RW * RC * 2, RH * RW * RC * 2, static_cast<cuuint64_t>(cap) * RH * RW * RC * 2};
+                encode(&rt.mapRes, tensors[c.res_tensor].buf.p, 5, dims, str, box);
+                rt.has_res = true;
+            }
         }
         memset(rt.mapHalo, 0, sizeof(rt.mapHalo));
         if (c.halo) {
@@ -678,15 +705,15 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
 namespace {
 
 template <int BN, int NP>
-void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap* mO, const ConvParams& p, int ctas,
-                            cudaStream_t s) {
+void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap* mO, const CUtensorMap& mR,
+                            const ConvParams& p, int ctas, cudaStream_t s) {
     using Cfg = ConvCfg<BN, NP>;
     static bool configured = false;
     if (!configured) {
         P2P_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES_P));
         configured = true;
     }
-    conv_tc_persistent_kernel<BN, NP><<<ctas, 64 + kEpiThreads, Cfg::SMEM_BYTES_P, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO[0], mO[1], mO[2], mO[3], p);
+    conv_tc_persistent_kernel<BN, NP><<<ctas, 64 + kEpiThreads, Cfg::SMEM_BYTES_P, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO[0], mO[1], mO[2], mO[3], mR, p);
     P2P_CUDA(cudaGetLastError());
 }
 
@@ -833,20 +860,25 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     else if (c.BN == 64 && stages > 3) nst = stages - 1;
                     p.nst = nst;
                     p.epi_bufs = (p.tma_store && c.BN >= 64) ? std::min(3, 1 + (stages - nst) * stage_bytes / epi_bytes) : 1;
-                    if (const char* e = getenv("P2P_NST")) { p.nst = atoi(e); p.epi_bufs = 1; }
+                    if (res_tma && rt.has_res && p.tma_store && stages > 2 && (stages - 2) * stage_bytes >= 2 * epi_bytes) {
+                        p.res_tma = 1;  // two residual tiles live in the operand stages above the second
+                        p.nst = 2;
+                        p.epi_bufs = 1;
+                    }
+                    if (const char* e = getenv("P2P_NST")) { p.nst = atoi(e); p.epi_bufs = 1; p.res_tma = 0; }
                 }
                 const int ctas = std::min<long long>(static_cast<long long>(grid.x) * grid.y * grid.z, num_sms);
                 if (c.BN == 256) {
-                    if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
-                    else launch_conv_persistent<256, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    if (np == 2) launch_conv_persistent<256, 2>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
+                    else launch_conv_persistent<256, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
                 } else if (np == 2) {
-                    if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
-                    else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
-                    else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    if (c.BN == 128) launch_conv_persistent<128, 2>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 2>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
+                    else launch_conv_persistent<16, 2>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
                 } else {
-                    if (c.BN == 128) launch_conv_persistent<128, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
-                    else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
-                    else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, rt.mapOut, p, ctas, s);
+                    if (c.BN == 128) launch_conv_persistent<128, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
+                    else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
+                    else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
                 }
             } else if (np == 2) {
                 if (c.BN == 128) launch_conv<128, 2>(rt.mapA, mc.mapB, p, grid, s);

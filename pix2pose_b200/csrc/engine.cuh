@@ -96,12 +96,13 @@ class Engine {
     std::vector<Tensor> tensors;
     DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
     DevBuf<float> partial;       // split-K scratch [slices][cap][Cout_pad]
-    struct ConvRt { DevBuf<int4> kit, slabs; CUtensorMap mapA[4]; CUtensorMap mapHalo[2]; CUtensorMap mapOut[4]; bool has_out = false; };
+    struct ConvRt { DevBuf<int4> kit, slabs; CUtensorMap mapA[4]; CUtensorMap mapHalo[2]; CUtensorMap mapOut[4]; bool has_out = false; CUtensorMap mapRes; bool has_res = false; };
     std::vector<ConvRt> conv_rt;
     int num_sms = 148;
     bool prof_layers = false; // print per-launch times in profile mode (P2P_PROF_LAYERS)
     int epi_nk = 8;           // layers with at most this many k-iterations per tile trade operand stages for output staging tiles (P2P_EPI_NK)
     int single_acc_steps = 40;  // accumulation chains up to this many k16 steps use one TMEM accumulator (P2P_SINGLE_ACC_STEPS)
+    bool res_tma = true;      // residual tiles by TMA into shared memory (P2P_RES_TMA=0 = per-thread loads)
     bool tma_store = true;    // TMA-store epilogue in the persistent kernel (default; P2P_TMA_STORE=0 = direct 16-byte stores)
     bool use_halo = false;    // conv_tc_halo_kernel for eligible convs (P2P_HALO=1)
     bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
