@@ -221,6 +221,22 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
             concat_off += s.c_count;
         }
         c.kstart[1] = static_cast<int>(c.kit.size());
+    } else if (c.kind == K_STEM) {
+        // Direct stride-2 stem conv on the 4-channel padded input (net_kernels.cuh stem_convert_kernel).  One k-iteration
+        // per kernel row kh; its K slice is the window (kw, c4) = ksize * 4 fp16 values starting at padded pixel 2*ox, which
+        // the overlapping tensor-map views 7 / 8 (even / odd input rows) deliver as the "channel" dimension.  Input row
+        // 2*oy + kh - pad = 2*(oy + dy) + parity; rows outside the image are zero-filled by TMA.
+        c.H = 64; c.W = 64;
+        const SrcSpec& s = c.srcs[0];
+        const int pad = c.ksize == 7 ? 3 : 1;  // ZeroPadding2D(3)+valid (resnet50_mod.py:200) / TF 'same' k5 s2: 1 before
+        c.maps.push_back({s.tensor, 7, 64});
+        c.maps.push_back({s.tensor, 8, 64});
+        for (int kh = 0; kh < c.ksize; ++kh) {
+            const int d = kh - pad, par = ((d % 2) + 2) % 2, dy = (d - par) / 2;
+            c.kit.push_back(make_int4(par, dy, 0, 0));
+            c.kw.push_back({kh, -1, 0, c.ksize * 4});
+        }
+        c.kstart[1] = static_cast<int>(c.kit.size());
     } else if (c.kind == K_CONV_S2) {
         c.H = t0.H / 2; c.W = t0.W / 2;
         const SrcSpec& s = c.srcs[0];
@@ -333,15 +349,28 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
 
 }  // namespace
 
+// padded row width of the stem input in pixels: the last window starts at pixel 2 * 63 and is 16 pixels wide
+constexpr int kStemWp = 144;
+static bool stem_direct() {
+    const char* e = getenv("P2P_STEM_DIRECT");  // 0 = im2col + 1x1 GEMM (the first implementation)
+    return !e || atoi(e) != 0;
+}
+
 Plan build_plan(int backbone) {
     Plan P;
     P.backbone = backbone;
     PlanBuilder B(P);
     if (backbone == BB_RESNET50) {
-        const int patches = B.T("patches", 64, 64, 192);
-        P.steps.push_back({S_IM2COL, patches, 7, 3, 192});
         const int f1 = B.T("f1", 64, 64, 64);
-        B.conv("conv1", K_PATCH, 7, {B.all(patches)}, {{"conv1", "bn_conv1"}}, f1, ACT_RELU);
+        if (stem_direct()) {
+            const int xpad = B.T("xpad", 128, kStemWp, 4);
+            P.steps.push_back({S_STEMCVT, xpad, 3, 0, 0});
+            B.conv("conv1", K_STEM, 7, {B.all(xpad)}, {{"conv1", "bn_conv1"}}, f1, ACT_RELU);
+        } else {
+            const int patches = B.T("patches", 64, 64, 192);
+            P.steps.push_back({S_IM2COL, patches, 7, 3, 192});
+            B.conv("conv1", K_PATCH, 7, {B.all(patches)}, {{"conv1", "bn_conv1"}}, f1, ACT_RELU);
+        }
         const int pool = B.T("pool1", 32, 32, 64);
         P.steps.push_back({S_MAXPOOL, f1, pool, 0, 0});
         int x = B.bottleneck(pool, 2, 'a', 64, 256, 1, true);
@@ -355,11 +384,17 @@ Plan build_plan(int backbone) {
         B.conv("conv4", K_CONV_S2, 5, {B.all(f3)}, {{"conv4_1", "bn_conv4_1"}, {"conv4_2", "bn_conv4_2"}}, f4, ACT_LRELU);
         B.decoder(f4, {f3, 0, 128}, {f2, 0, 128}, {f1, 0, 32});  // ae_model.py:186-188 channel slices
     } else {
-        const int patches = B.T("patches", 64, 64, 128);
-        P.steps.push_back({S_IM2COL, patches, 5, 1, 128});
         const int f1 = B.T("f1", 64, 64, 128), f2 = B.T("f2", 32, 32, 256), f3 = B.T("f3", 16, 16, 256);
         const int f4 = B.T("f4", 8, 8, 512);
-        B.conv("conv1", K_PATCH, 5, {B.all(patches)}, {{"conv1_1", "bn_conv1_1"}, {"conv1_2", "bn_conv1_2"}}, f1, ACT_LRELU);
+        if (stem_direct()) {
+            const int xpad = B.T("xpad", 128, kStemWp, 4);
+            P.steps.push_back({S_STEMCVT, xpad, 1, 0, 0});
+            B.conv("conv1", K_STEM, 5, {B.all(xpad)}, {{"conv1_1", "bn_conv1_1"}, {"conv1_2", "bn_conv1_2"}}, f1, ACT_LRELU);
+        } else {
+            const int patches = B.T("patches", 64, 64, 128);
+            P.steps.push_back({S_IM2COL, patches, 5, 1, 128});
+            B.conv("conv1", K_PATCH, 5, {B.all(patches)}, {{"conv1_1", "bn_conv1_1"}, {"conv1_2", "bn_conv1_2"}}, f1, ACT_LRELU);
+        }
         B.conv("conv2", K_CONV_S2, 5, {B.all(f1)}, {{"conv2_1", "bn_conv2_1"}, {"conv2_2", "bn_conv2_2"}}, f2, ACT_LRELU);
         B.conv("conv3", K_CONV_S2, 5, {B.all(f2)}, {{"conv3_1", "bn_conv3_1"}, {"conv3_2", "bn_conv3_2"}}, f3, ACT_LRELU);
         B.conv("conv4", K_CONV_S2, 5, {B.all(f3)}, {{"conv4_1", "bn_conv4_1"}, {"conv4_2", "bn_conv4_2"}}, f4, ACT_LRELU);
@@ -415,9 +450,12 @@ void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const 
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-        throw Error(P2P_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu)",
+        throw Error(P2P_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu strides %llu %llu %llu %llu box %u %u %u %u %u base %p)",
                                       static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-                                      (unsigned long long)dims[2], (unsigned long long)dims[3]));
+                                      (unsigned long long)dims[2], (unsigned long long)dims[3], (unsigned long long)dims[4],
+                                      (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+                                      (unsigned long long)strides_bytes[2], (unsigned long long)strides_bytes[3], box[0], box[1], box[2],
+                                      box[3], box[4], base));
 }
 
 }  // namespace
@@ -476,6 +514,12 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
             if (rq.view == 0) {
                 dims[0] = rq.climit; dims[1] = W; dims[2] = H; dims[3] = cap; dims[4] = np;
                 str[0] = C * 2; str[1] = W * C * 2; str[2] = H * W * C * 2; str[3] = plane_b;
+            } else if (rq.view == 7 || rq.view == 8) {
+                // stem input (N, 128, Wp, 4): dim0 = 64 consecutive fp16 values (16 pixels), dim1 = output column (window start
+                // advances 2 pixels = 16 bytes: overlapping windows), dim2 = input rows of one parity
+                base += static_cast<size_t>(rq.view - 7) * W * C;
+                dims[0] = 64; dims[1] = 64; dims[2] = H / 2; dims[3] = cap; dims[4] = np;
+                str[0] = 16; str[1] = 2 * W * C * 2; str[2] = H * W * C * 2; str[3] = plane_b;
             } else if (rq.view >= 1 && rq.view <= 4) {
                 const int py = (rq.view - 1) >> 1, px = (rq.view - 1) & 1;
                 base += (static_cast<size_t>(py) * W + px) * C;
@@ -638,6 +682,10 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
                         } else if (c.kind == K_PATCH) {
                             if (cin >= l.shape[0] * l.shape[1] * l.shape[2]) continue;
                             v = q.k[static_cast<size_t>(cin) * l.shape[3] + co];
+                        } else if (c.kind == K_STEM) {
+                            const int kx = j / 4, ci = j % 4;  // K slice of a kernel row: (kw, channel padded to 4)
+                            if (ci == 3) continue;
+                            v = q.k[((static_cast<size_t>(kw.kh) * l.shape[1] + kx) * l.shape[2] + ci) * l.shape[3] + co];
                         } else if (l.kind == L_CONVT) {
                             v = q.k[((static_cast<size_t>(kw.kh) * 5 + kw.kw) * l.shape[2] + co) * l.shape[3] + cin];
                         } else {
@@ -763,6 +811,13 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             const long long total = static_cast<long long>(n) * 64 * 64 * (st.d / 8);
             const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 22));
             im2col_stem_kernel<<<blocks, 256, 0, s>>>(x_dev, tensors[st.a].buf.p, tensors[st.a].plane, n, st.b, st.c, st.d, n_active);
+            P2P_CUDA(cudaGetLastError());
+            ++launches;
+            mark(1);
+        } else if (st.kind == S_STEMCVT) {
+            const long long total = static_cast<long long>(n) * 128 * 128;
+            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 22));
+            stem_convert_kernel<<<blocks, 256, 0, s>>>(x_dev, tensors[st.a].buf.p, tensors[st.a].plane, n, plan.tensors[st.a].W, st.b, n_active);
             P2P_CUDA(cudaGetLastError());
             ++launches;
             mark(1);

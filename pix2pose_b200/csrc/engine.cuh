@@ -28,7 +28,7 @@ std::vector<LayerDef> layer_table(int backbone);
 size_t param_count(int backbone);
 int parse_backbone(const char* s);
 
-enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4, K_CONVT_FUSED = 5 };
+enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4, K_CONVT_FUSED = 5, K_STEM = 6 };
 
 struct SrcSpec { int tensor, c_begin, c_count; };
 struct WPart { std::string layer, bn; };
@@ -57,8 +57,8 @@ struct ConvSpec {
 
 struct TensorSpec { std::string name; int H, W, C; };
 
-enum StepKind : int { S_IM2COL = 0, S_CONV = 1, S_MAXPOOL = 2 };
-struct Step { int kind; int a, b, c, d; };  // CONV: a = conv index; IM2COL: a=out tensor,b=ks,c=pad ; MAXPOOL: a=in,b=out
+enum StepKind : int { S_IM2COL = 0, S_CONV = 1, S_MAXPOOL = 2, S_STEMCVT = 3 };
+struct Step { int kind; int a, b, c, d; };  // CONV: a = conv index; IM2COL: a=out tensor,b=ks,c=pad ; MAXPOOL: a=in,b=out ; STEMCVT: a=out tensor,b=left pad (pixels)
 
 struct Plan {
     int backbone;

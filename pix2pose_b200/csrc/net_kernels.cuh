@@ -45,6 +45,33 @@ __global__ void im2col_stem_kernel(const float* __restrict__ x, __half* __restri
     }
 }
 
+// Stem input for the direct (no im2col) first convolution: x (N,128,128,3) fp32 -> (N,128,Wp,4) fp16 hi/lo, channel 3 = 0,
+// real pixels at columns pl .. pl+127 (the columns around them stay zero from the allocation memset: they are the
+// horizontal zero padding).  With 4 channels a pixel is 8 bytes, so the 16-byte-strided, overlapping TMA view
+// "window of 16 pixels starting at pixel 2*ox" (engine.cu, K_STEM) presents every kernel ROW (kw, c) of a stride-2 stem
+// convolution as the contiguous K slice of output pixel ox -- the 805 MB patch matrix of the im2col path is never built.
+__global__ void stem_convert_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane, int N, int Wp, int pl,
+                                    const int* __restrict__ n_active) {
+    int n_limit = N;
+    if (n_active) n_limit = min(n_limit, *n_active);
+    const long long total = static_cast<long long>(n_limit) * 128 * 128;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xx = static_cast<int>(i & 127);
+        const long long row = i >> 7;  // n * 128 + y
+        const float r = __ldg(x + i * 3), g = __ldg(x + i * 3 + 1), b = __ldg(x + i * 3 + 2);
+        const __half2 h01 = __floats2half2_rn(r, g), h23 = __floats2half2_rn(b, 0.f);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(r - f01.x, g - f01.y), l23 = __floats2half2_rn(b - f23.x, 0.f);
+        const long long o = (row * Wp + pl + xx) * 4;
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(out + o) = hv;
+        if (plane) *reinterpret_cast<uint2*>(out + o + plane) = lv;
+    }
+}
+
 // MaxPooling2D(3x3, s2, 'same') on (N,64,64,64) -> (N,32,32,64): TF pads 0 before / 1 after with -inf.
 // One thread handles 8 channels (16-byte loads / stores per plane).
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, long long in_plane, __half* __restrict__ out,
