@@ -13,6 +13,28 @@
 
 namespace p2p {
 
+// TMEM plan and MMA schedule of the persistent kernel.
+//
+// fp16x3 keeps the hi*hi products and the 2^-11-times-smaller cross terms (lo*hi + hi*lo) in two separate accumulators
+// (the tensor core rounds the fp32 accumulator toward zero after every MMA; keeping the small terms out of the big chain
+// is what holds the 1e-3 tolerance, see ConvCfg).  For tiles of up to 128 columns the two accumulators sit side by side
+// in TMEM, [hh: BN columns][cross: BN columns], and the weight tile sits in shared memory as [W_hi: BN rows][W_lo: BN
+// rows], so ONE MMA of width 2 * BN computes A_hi * [W_hi; W_lo]^T = (hi*hi | hi*lo) into both, and a second MMA of
+// width BN adds A_lo * W_hi^T to the cross half: two instructions and two A-operand reads per k16 step instead of
+// three (narrow tiles are instruction-bound: the heads layer, N = 16, went from 521 to 3xx us per 256 crops).
+// BN = 256 cannot be widened (N <= 256) and issues the three MMAs separately.
+// Whenever two accumulator sets fit into the 512 TMEM columns they are double-buffered: the MMA warp starts tile i + 1
+// in the other set while the epilogue warps drain tile i.
+template <int BN, int NP>
+struct PersCfg {
+    static constexpr bool CONCAT = NP == 2 && BN <= 128;        // (hi*hi | hi*lo) in one MMA of width 2 * BN
+    static constexpr int ACC_STRIDE = BN;                        // TMEM columns between the hh and the cross accumulator
+    static constexpr int NACC = NP == 2 ? 2 : 1;
+    static constexpr int BUF_COLS = NACC * ACC_STRIDE < 32 ? 32 : NACC * ACC_STRIDE;  // TMEM columns of one accumulator set
+    static constexpr int NBUF = 2 * BUF_COLS <= 512 ? 2 : 1;     // accumulator sets (BN = 256 fp16x3 fills TMEM with one)
+    static constexpr uint32_t TMEM_COLS = NBUF * BUF_COLS <= 32 ? 32 : (NBUF * BUF_COLS <= 64 ? 64 : (NBUF * BUF_COLS <= 128 ? 128 : (NBUF * BUF_COLS <= 256 ? 256 : 512)));
+};
+
 struct TileCoord {
     int n0, y0, x0, nt0, z, kbeg, nk;
     bool live;
@@ -101,6 +123,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                                               int nl, int n_limit, EpiState& e, const CUtensorMap* mO0, const CUtensorMap* mO1,
                                               const CUtensorMap* mO2, const CUtensorMap* mO3, int etid) {
     using Cfg = ConvCfg<BN, NP>;
+    using PC = PersCfg<BN, NP>;
     constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns handled per pass (all threads)
     constexpr int NPASS = BN > 128 ? BN / 128 : 1;
     constexpr int NSL = NCOL >= 64 ? NCOL / 64 : 1;               // 64-channel slices per pass
@@ -114,7 +137,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     const int oy = y * p.sy + p.oy_off[zi], ox = x * p.sx + p.ox_off[zi];
     const long long pix = (static_cast<long long>(n) * p.OH + oy) * p.OW + ox;
     const bool tstore = BN >= 64 && p.tma_store && !splitk && p.act != ACT_HEADS;
-    const bool nacc3 = Cfg::NACC == 3 && !p.single_acc, nacc2 = Cfg::NACC >= 2 && !p.single_acc;
+    const bool nacc2 = PC::NACC == 2 && !p.single_acc;
     const float slope = p.act == ACT_LRELU ? 0.3f : (p.act == ACT_RELU ? 0.f : 1.f);  // act(v) = max(v, slope * v)
     const int nbuf = p.epi_bufs;
     const bool res_tma = BN >= 64 && p.res_tma != 0;
@@ -144,13 +167,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-                if (nacc3) {
-                    uint32_t v1[16], v2[16];
-                    tmem_ld_32x16(taddr + Cfg::ACC_STRIDE, v1);
-                    tmem_ld_32x16(taddr + 2 * Cfg::ACC_STRIDE, v2);
+                if (nacc2) {
+                    uint32_t v1[16];
+                    tmem_ld_32x16(taddr + PC::ACC_STRIDE, v1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = (acc[j] + __uint_as_float(v1[j])) + __uint_as_float(v2[j]);
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v1[j]);
                 }
             }
         } else {
@@ -163,13 +185,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[sl * 32 + j] = __uint_as_float(v[j]);
                 if (nacc2) {
-                    tmem_ld_32x32(tcol + Cfg::ACC_STRIDE, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
-                }
-                if (nacc3) {
-                    tmem_ld_32x32(tcol + 2 * Cfg::ACC_STRIDE, v);
+                    tmem_ld_32x32(tcol + PC::ACC_STRIDE, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[sl * 32 + j] += __uint_as_float(v[j]);
@@ -313,6 +329,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                           const __grid_constant__ CUtensorMap mO3, const __grid_constant__ CUtensorMap mR,
                           const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN, NP>;
+    using PC = PersCfg<BN, NP>;
     constexpr int STAGES = Cfg::STAGES;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -329,9 +346,9 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
     uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;  // output staging (BN >= 64), 1024-B aligned
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + (BN >= 64 ? Cfg::EPI_BYTES : 0));
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-    uint64_t* res_bar = tmem_empty_bar + 1;  // residual tiles (p.res_tma): [0..1] full, [2..3] empty
+    uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]: one per accumulator set
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+    uint64_t* res_bar = tmem_empty_bar + 2;  // residual tiles (p.res_tma): [0..1] full, [2..3] empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [BN] + [BN] (BN <= 128, Cfg::CONST_BYTES)
 
@@ -342,12 +359,14 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, kEpiWarps);  // one arrival per epilogue warp
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full_bar[b], 1);
+            mbar_init(&tmem_empty_bar[b], kEpiWarps);  // one arrival per epilogue warp
+        }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     } else if (warp == 2) {
-        tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+        tmem_alloc<PC::TMEM_COLS>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -407,16 +426,21 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         // same reason the per-iteration k16-step counts come from the kernel parameters (constant bank -> uniform
         // registers), not from global memory.
         constexpr uint32_t idesc = umma_idesc_f16(128, BN < 16 ? 16 : BN);
+        constexpr uint32_t idesc2 = umma_idesc_f16(128, PC::CONCAT ? 2 * BN : BN);  // A_hi * [W_hi; W_lo]^T
         const bool one_acc = p.single_acc != 0;
-        const uint32_t cross = one_acc ? 0u : (Cfg::NACC - 1) * Cfg::ACC_STRIDE;
-        const bool split_hh = Cfg::NACC == 3 && !one_acc;
+        const uint32_t cross = one_acc ? 0u : PC::ACC_STRIDE;
         const uint32_t smem_a0 = smem_u32(smem);
         int st = 0, tile_i = 0;
         uint32_t ph = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            mbar_wait(tmem_empty_bar, (tile_i & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
+            // accumulator set of this tile; the epilogue has drained the tile that used it last (NBUF tiles ago)
+            const uint32_t buf = PC::NBUF == 2 ? (tile_i & 1) : 0;
+            const uint32_t use = PC::NBUF == 2 ? (tile_i >> 1) : tile_i;
+            mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * PC::BUF_COLS;
             int g = 0;
             for (int it = 0; it < tc.nk; ++it) {
                 const int ksteps = p.ksteps_tab[tc.kbeg + it];
@@ -430,23 +454,28 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                     const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
                     if (NP == 2) {
                         const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
-                        const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                        const uint32_t d_hh = split_hh ? tmem_base + (g & 1) * Cfg::ACC_STRIDE : tmem_base;
-                        const uint32_t acc_hh = split_hh ? (g >= 2 ? 1u : 0u) : (g > 0 ? 1u : 0u);
-                        const uint32_t acc_x = (g > 0 || one_acc) ? 1u : 0u;
-                        if (elect_one()) {
-                            umma_f16(d_hh, a_hi, b_hi, idesc, acc_hh);
-                            umma_f16(tmem_base + cross, a_lo, b_hi, idesc, acc_x);
-                            umma_f16(tmem_base + cross, a_hi, b_lo, idesc, 1u);
+                        const uint32_t acc_g = g > 0 ? 1u : 0u;
+                        if (PC::CONCAT && !one_acc) {
+                            if (elect_one()) {
+                                umma_f16(tacc, a_hi, b_hi, idesc2, acc_g);          // hi*hi -> [0, BN), hi*lo -> [BN, 2 BN)
+                                umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);     // lo*hi -> [BN, 2 BN)
+                            }
+                        } else {
+                            const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
+                            if (elect_one()) {
+                                umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
+                                umma_f16(tacc + cross, a_lo, b_hi, idesc, (g > 0 || one_acc) ? 1u : 0u);
+                                umma_f16(tacc + cross, a_hi, b_lo, idesc, 1u);
+                            }
                         }
                     } else {
-                        if (elect_one()) umma_f16(tmem_base, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
+                        if (elect_one()) umma_f16(tacc, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                     }
                 }
                 if (elect_one()) umma_commit(&empty_bar[st]);
                 if (++st == nst) { st = 0; ph ^= 1; }
             }
-            if (elect_one()) umma_commit(tmem_full_bar);
+            if (elect_one()) umma_commit(&tmem_full_bar[buf]);
             ++tile_i;
         }
         __syncwarp();
@@ -472,8 +501,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tc = decode_tile<BN>(p, t, n_limit);
             if (!tc.live) continue;
-            epilogue_tile<BN, NP>(p, taddr, lane, tmem_full_bar, tile_i & 1, tmem_empty_bar, tc, hl, wl, nl, n_limit, e, &mO0, &mO1,
-                                  &mO2, &mO3, etid);
+            const uint32_t buf = PC::NBUF == 2 ? (tile_i & 1) : 0;
+            const uint32_t use = PC::NBUF == 2 ? (tile_i >> 1) : tile_i;
+            epilogue_tile<BN, NP>(p, taddr + buf * PC::BUF_COLS, lane, &tmem_full_bar[buf], use & 1, &tmem_empty_bar[buf], tc, hl, wl, nl,
+                                  n_limit, e, &mO0, &mO1, &mO2, &mO3, etid);
             ++tile_i;
         }
         if (threadIdx.x == 64) bulk_wait_all();  // outstanding TMA stores complete before the CTA retires
@@ -481,7 +512,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 2) tmem_dealloc<PC::TMEM_COLS>(tmem_base);
 }
 
 }  // namespace p2p

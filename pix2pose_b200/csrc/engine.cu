@@ -7,7 +7,7 @@
 #include <algorithm>
 #include <mutex>
 
-#include "conv_tc_halo.cuh"
+#include "conv_tc_persistent.cuh"
 #include "net_kernels.cuh"
 
 namespace p2p {
@@ -305,21 +305,6 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         }
         c.kstart[1] = static_cast<int>(c.kit.size());
     }
-    c.halo = false;
-    c.slabs.clear();
-    if (c.kind == K_CONV && c.ksize >= 3 && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() <= 2 && c.Cout >= 64) {
-        c.halo = true;
-        int src_base = 0;
-        for (size_t si = 0; si < c.srcs.size(); ++si) {
-            const SrcSpec& sp = c.srcs[si];
-            const int nch = chunks(sp.c_count);
-            for (int ch = 0; ch < nch; ++ch) {
-                const int nvalid = std::min(64, sp.c_count - ch * 64);
-                c.slabs.push_back(make_int4(static_cast<int>(si) | (((nvalid + 15) / 16) << 8), sp.c_begin + ch * 64, src_base + ch, nch));
-            }
-            src_base += c.ksize * c.ksize * nch;
-        }
-    }
     if (c.kind == K_CONVT_FUSED) {
         if (c.act == ACT_HEADS) { c.BN = 16; c.Cout_pad = 16; }
         else { c.BN = 128; c.Cout_pad = (c.Cout + 127) / 128 * 128; }
@@ -335,8 +320,10 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         // layers stay at 128: they are epilogue-bound and BN = 256 leaves no shared memory for staging tiles.
         const char* e = getenv("P2P_BN256");
         const int min_kit = e ? atoi(e) : 100;   // P2P_BN256=0 disables, otherwise = minimum k-iterations per tile
-        if (min_kit > 0 && c.BN == 128 && c.Cout % 256 == 0 && c.splitk <= 1 && c.phases == 1 && c.kind != K_CONVT_FUSED &&
-            static_cast<int>(c.kit.size()) >= min_kit) {
+        static const bool fused256 = !getenv("P2P_BN256_FUSED") || atoi(getenv("P2P_BN256_FUSED")) != 0;  // convT3: 659 -> 592 us per 256 crops
+        if (min_kit > 0 && c.BN == 128 && c.Cout % 256 == 0 && c.splitk <= 1 && c.phases == 1 &&
+            (c.kind != K_CONVT_FUSED || (fused256 && c.act != ACT_HEADS)) &&
+            static_cast<int>(c.kit.size()) >= (c.kind == K_CONVT_FUSED ? 1 : min_kit)) {
             c.BN = 256; c.Cout_pad = c.Cout;
         }
     }
@@ -472,7 +459,6 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
-    if (const char* e = getenv("P2P_HALO")) use_halo = atoi(e) != 0;
     if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
     if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
     if (const char* e = getenv("P2P_EPI_NK")) epi_nk = atoi(e);
@@ -577,21 +563,6 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 encode(&rt.mapRes, tensors[c.res_tensor].buf.p, 5, dims, str, box);
                 rt.has_res = true;
             }
-        }
-        memset(rt.mapHalo, 0, sizeof(rt.mapHalo));
-        if (c.halo) {
-            rt.slabs.upload(c.slabs.data(), c.slabs.size());
-            const int pad = (c.ksize - 1) / 2;
-            for (size_t si = 0; si < c.srcs.size(); ++si) {
-                const SrcSpec& sp = c.srcs[si];
-                const TensorSpec& t = plan.tensors[sp.tensor];
-                const cuuint64_t C = t.C, W = t.W, H = t.H;
-                cuuint64_t dims[5] = {(cuuint64_t)(sp.c_begin + sp.c_count), W, H, (cuuint64_t)cap, (cuuint64_t)np};
-                cuuint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, static_cast<cuuint64_t>(cap) * H * W * C * 2};
-                cuuint32_t box[5] = {64, 8, (cuuint32_t)(16 + 2 * pad), 1, (cuuint32_t)np};
-                encode(&rt.mapHalo[si], tensors[sp.tensor].buf.p, 5, dims, str, box);
-            }
-            if (c.srcs.size() < 2) rt.mapHalo[1] = rt.mapHalo[0];
         }
     }
     P2P_CUDA(cudaDeviceSynchronize());
@@ -766,18 +737,6 @@ void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const 
 }
 
 template <int BN, int NP>
-void launch_conv_halo(const CUtensorMap* mH, const CUtensorMap& mB, const ConvParams& p, int ctas, cudaStream_t s) {
-    using HC = HaloCfg<BN, NP>;
-    static bool configured = false;
-    if (!configured) {
-        P2P_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, HC::SMEM_BYTES));
-        configured = true;
-    }
-    conv_tc_halo_kernel<BN, NP><<<ctas, 64 + kEpiThreads, HC::SMEM_BYTES, s>>>(mH[0], mH[1], mB, p);
-    P2P_CUDA(cudaGetLastError());
-}
-
-template <int BN, int NP>
 void launch_conv(const CUtensorMap* mA, const CUtensorMap& mB, const ConvParams& p, dim3 grid, cudaStream_t s) {
     using Cfg = ConvCfg<BN, NP>;
     static bool configured = false;
@@ -885,25 +844,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
             P2P_CHECK(c.BN != 256 || persistent, "BN = 256 tiles need the persistent kernel");
-            if (use_halo && c.halo) {
-                p.tw = 8; p.th = 16; p.nb = 1;
-                p.tiles_x = c.W / 8; p.tiles_y = c.H / 16;
-                p.grid_m = p.tiles_x * p.tiles_y * n; p.grid_z = 1;
-                p.halo_ksize = c.ksize;
-                p.kit = rt.slabs.p;
-                p.kstart[0] = 0;
-                for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
-                const int ctas = std::min<long long>(static_cast<long long>(p.grid_m) * p.grid_n, num_sms);
-                if (np == 2) {
-                    if (c.BN == 256) launch_conv_halo<256, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
-                    else if (c.BN == 128) launch_conv_halo<128, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
-                    else launch_conv_halo<64, 2>(rt.mapHalo, mc.mapB, p, ctas, s);
-                } else {
-                    if (c.BN == 256) launch_conv_halo<256, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
-                    else if (c.BN == 128) launch_conv_halo<128, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
-                    else launch_conv_halo<64, 1>(rt.mapHalo, mc.mapB, p, ctas, s);
-                }
-            } else if (persistent) {
+            if (persistent) {
                 p.tma_store = (tma_store && rt.has_out) ? 1 : 0;
                 {
                     // epilogue-bound layers (few k-iterations per tile) run on fewer operand stages and use the freed

@@ -46,8 +46,6 @@ struct ConvSpec {
     int Cin = 0, Cout = 0, Cout_pad = 0, BN = 0;
     int kstart[5] = {0, 0, 0, 0, 0};
     int splitk = 1, splitk_chunk = 0;  // K slices (Dense layers whose M x N grid cannot fill the GPU)
-    bool halo = false;                 // eligible for conv_tc_halo_kernel (k x k stride-1 conv, W % 8 == 0, H % 16 == 0)
-    std::vector<int4> slabs;           // halo kernel: one entry per (source, 64-channel chunk)
     int oy_off[4] = {0, 0, 0, 0}, ox_off[4] = {0, 0, 0, 0}, sy = 1, sx = 1;
     std::vector<int4> kit;
     std::vector<KWeight> kw;
@@ -96,7 +94,7 @@ class Engine {
     std::vector<Tensor> tensors;
     DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
     DevBuf<float> partial;       // split-K scratch [slices][cap][Cout_pad]
-    struct ConvRt { DevBuf<int4> kit, slabs; CUtensorMap mapA[4]; CUtensorMap mapHalo[2]; CUtensorMap mapOut[4]; bool has_out = false; CUtensorMap mapRes; bool has_res = false; };
+    struct ConvRt { DevBuf<int4> kit; CUtensorMap mapA[4]; CUtensorMap mapOut[4]; bool has_out = false; CUtensorMap mapRes; bool has_res = false; };
     std::vector<ConvRt> conv_rt;
     int num_sms = 148;
     bool prof_layers = false; // print per-launch times in profile mode (P2P_PROF_LAYERS)
@@ -104,7 +102,6 @@ class Engine {
     int single_acc_steps = 40;  // accumulation chains up to this many k16 steps use one TMEM accumulator (P2P_SINGLE_ACC_STEPS)
     bool res_tma = true;      // residual tiles by TMA into shared memory (P2P_RES_TMA=0 = per-thread loads)
     bool tma_store = true;    // TMA-store epilogue in the persistent kernel (default; P2P_TMA_STORE=0 = direct 16-byte stores)
-    bool use_halo = false;    // conv_tc_halo_kernel for eligible convs (P2P_HALO=1)
     bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
 
     // x_dev -> dec_dev / prob_dev for n <= cap crops; n_active (device int) optionally limits work further.

@@ -49,9 +49,10 @@ __device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t,
 }
 
 // ---- (1) hypotheses: RNG replay by thread 0, then one 5-point EPnP per thread
-__global__ void __launch_bounds__(kHypThreads, 4) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
-                                                                 const float* __restrict__ obj, const float* __restrict__ img,
-                                                                 double* __restrict__ hyp, int iters) {
+template <int MINB>
+__global__ void __launch_bounds__(kHypThreads, MINB) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
+                                                                    const float* __restrict__ obj, const float* __restrict__ img,
+                                                                    double* __restrict__ hyp, int iters) {
     extern __shared__ int s_idx[];
     const PnpProblem pr = probs[blockIdx.x];
     if (pr.n < 6) return;
@@ -406,18 +407,45 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     P2P_CHECK(confidence > 0 && confidence < 1, "confidence must be in (0,1)");
     ensure(n_problems, iters);
     const float thr2 = static_cast<float>(static_cast<double>(reproj_err) * static_cast<double>(reproj_err));
-    ransac_hyp_kernel<<<n_problems, kHypThreads, iters * 5 * sizeof(int), s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    static const int hyp_minb = getenv("P2P_HYP_MINB") ? atoi(getenv("P2P_HYP_MINB")) : 3;   // occupancy knob: 3 blocks/SM (168 registers) measured fastest (4.2 -> 3.25 ms per 768 problems)
+    static const bool prof = getenv("P2P_PROF_PNP") && atoi(getenv("P2P_PROF_PNP")) != 0;       // per-kernel times to stderr
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto mark = [&](int i) {
+        if (!prof) return;
+        P2P_CUDA(cudaEventCreate(&ev[i]));
+        P2P_CUDA(cudaEventRecord(ev[i], s));
+    };
+    mark(0);
+    const size_t hyp_smem = iters * 5 * sizeof(int);
+    if (hyp_minb == 3) ransac_hyp_kernel<3><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    else if (hyp_minb == 5) ransac_hyp_kernel<5><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    else if (hyp_minb == 6) ransac_hyp_kernel<6><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    else if (hyp_minb == 8) ransac_hyp_kernel<8><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    else if (hyp_minb == 2) ransac_hyp_kernel<2><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    else ransac_hyp_kernel<4><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
     P2P_CUDA(cudaGetLastError());
+    mark(1);
     P2P_CHECK(max_n >= 0, "max_n must be the largest correspondence count of the batch");
     P2P_CUDA(cudaMemsetAsync(counts_.p, 0, sizeof(int) * static_cast<size_t>(n_problems) * iters, s));
     dim3 g(std::max(1, (max_n + kScoreTile - 1) / kScoreTile), n_problems);
     ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, thr2);
     P2P_CUDA(cudaGetLastError());
+    mark(2);
     ransac_select_kernel<<<n_problems, 256, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, best_.p, mask_dev,
                                                     results_dev, iters, thr2, confidence);
     P2P_CUDA(cudaGetLastError());
+    mark(3);
     epnp_refit_kernel<<<n_problems, kRefitThreads, 0, s>>>(problems_dev, obj_dev, img_dev, mask_dev, results_dev);
     P2P_CUDA(cudaGetLastError());
+    mark(4);
+    if (prof) {
+        P2P_CUDA(cudaStreamSynchronize(s));
+        float ms[4];
+        for (int i = 0; i < 4; ++i) P2P_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        fprintf(stderr, "pnp[%d problems, minb %d] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, hyp_minb, ms[0], ms[1],
+                ms[2], ms[3]);
+        for (auto e : ev) cudaEventDestroy(e);
+    }
     launches += 4;
 }
 
