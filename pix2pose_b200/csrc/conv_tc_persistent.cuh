@@ -40,13 +40,11 @@ struct TileCoord {
     bool live;
 };
 
+// tile (m, ny, z) of the launch grid -> coordinates
 template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int n_limit) {
+__device__ __forceinline__ TileCoord decode_mnz(const ConvParams& p, int m, int ny, int z, int n_limit) {
     TileCoord c;
-    const int m = t % p.grid_m;
-    const int r = t / p.grid_m;
-    const int ny = r % p.grid_n;
-    c.z = r / p.grid_n;
+    c.z = z;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int tn = m / tiles_per_img;
     const int trem = m - tn * tiles_per_img;
@@ -63,6 +61,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int
         c.nk = p.kstart[c.z + 1] - c.kbeg;
     }
     return c;
+}
+
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int n_limit) {
+    const int m = t % p.grid_m;
+    const int r = t / p.grid_m;
+    return decode_mnz<BN>(p, m, r % p.grid_n, r / p.grid_n, n_limit);
 }
 
 // Epilogue of one tile.  kEpiWarps = 8 warps (256 threads): warp w may only touch TMEM lanes (w % 4) * 32 .. + 31, so
@@ -121,7 +126,8 @@ template <int BN, int NP>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int lane, uint64_t* tmem_full_bar,
                                               uint32_t full_parity, uint64_t* tmem_empty_bar, const TileCoord& tc, int hl, int wl,
                                               int nl, int n_limit, EpiState& e, const CUtensorMap* mO0, const CUtensorMap* mO1,
-                                              const CUtensorMap* mO2, const CUtensorMap* mO3, int etid) {
+                                              const CUtensorMap* mO2, const CUtensorMap* mO3, int etid,
+                                              uint32_t tmem_empty_cluster_addr = 0) {
     using Cfg = ConvCfg<BN, NP>;
     using PC = PersCfg<BN, NP>;
     constexpr int NCOL = BN < 32 ? 16 : (BN > 128 ? 128 : BN);  // accumulator columns handled per pass (all threads)
@@ -195,7 +201,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         if (pass == NPASS - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);  // TMEM is free: the next tile's MMAs may start
+            if (lane == 0) {  // TMEM is free: the next tile's MMAs may start
+                if (tmem_empty_cluster_addr) mbar_arrive_cluster(tmem_empty_cluster_addr);  // CTA pair: the leader's barrier
+                else mbar_arrive(tmem_empty_bar);
+            }
         }
 
         if (BN < 64) {
@@ -463,9 +472,11 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                         } else {
                             const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
                             if (elect_one()) {
+                                // same order of additions into the cross accumulator as the widened scheme above
+                                // (hi*lo, then lo*hi), so every kernel variant produces identical bits
                                 umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
-                                umma_f16(tacc + cross, a_lo, b_hi, idesc, (g > 0 || one_acc) ? 1u : 0u);
-                                umma_f16(tacc + cross, a_hi, b_lo, idesc, 1u);
+                                umma_f16(tacc + cross, a_hi, b_lo, idesc, (g > 0 || one_acc) ? 1u : 0u);
+                                umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);
                             }
                         }
                     } else {

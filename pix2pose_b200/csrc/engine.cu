@@ -7,7 +7,7 @@
 #include <algorithm>
 #include <mutex>
 
-#include "conv_tc_persistent.cuh"
+#include "conv_tc_pair.cuh"
 #include "net_kernels.cuh"
 
 namespace p2p {
@@ -459,6 +459,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
+    if (const char* e = getenv("P2P_PAIR")) pair = atoi(e) != 0;
     if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
     if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
     if (const char* e = getenv("P2P_EPI_NK")) epi_nk = atoi(e);
@@ -715,6 +716,12 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
         cuuint64_t str[3] = {128, (cuuint64_t)c.Cout_pad * 128, (cuuint64_t)c.Cout_pad * 128 * np};
         cuuint32_t box[4] = {64, (cuuint32_t)c.BN, (cuuint32_t)np, 1};
         encode(&mc.mapB, mc.packed.p, 4, dims, str, box);
+        if (c.BN >= 128) {
+            cuuint32_t boxh[4] = {64, (cuuint32_t)(c.BN / 2), (cuuint32_t)np, 1};
+            encode(&mc.mapBh, mc.packed.p, 4, dims, str, boxh);
+        } else {
+            mc.mapBh = mc.mapB;
+        }
     }
     P2P_CUDA(cudaDeviceSynchronize());
 }
@@ -733,6 +740,32 @@ void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const 
         configured = true;
     }
     conv_tc_persistent_kernel<BN, NP><<<ctas, 64 + kEpiThreads, Cfg::SMEM_BYTES_P, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO[0], mO[1], mO[2], mO[3], mR, p);
+    P2P_CUDA(cudaGetLastError());
+}
+
+// CTA-pair kernel: grid = 2 x (clusters that can be resident at once, at most one per tile pair)
+template <int BN, int NP>
+void launch_conv_pair(const CUtensorMap* mA, const CUtensorMap& mBh, const CUtensorMap* mO, const ConvParams& p, int pairs, cudaStream_t s) {
+    using Cfg = PairCfg<BN, NP>;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        P2P_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2, 1, 1);
+        cfg.blockDim = dim3(64 + kEpiThreads, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, conv_tc_pair_kernel<BN, NP>, &cfg) != cudaSuccess || max_clusters < 1) {
+            (void)cudaGetLastError();
+            int dev = 0, sms = 0;
+            P2P_CUDA(cudaGetDevice(&dev));
+            P2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            max_clusters = std::max(1, sms / 2);
+        }
+        if (getenv("P2P_PROF_LAYERS")) fprintf(stderr, "[pair<%d,%d>] resident clusters %d\n", BN, NP, max_clusters);
+    }
+    const int clusters = std::min(pairs, max_clusters);
+    conv_tc_pair_kernel<BN, NP><<<2 * clusters, 64 + kEpiThreads, Cfg::SMEM_BYTES, s>>>(mA[0], mA[1], mA[2], mA[3], mBh, mO[0], mO[1], mO[2], mO[3], p);
     P2P_CUDA(cudaGetLastError());
 }
 
@@ -844,7 +877,24 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
             P2P_CHECK(c.BN != 256 || persistent, "BN = 256 tiles need the persistent kernel");
-            if (persistent) {
+            // N = 128 tiles stay on the single-CTA kernel: a cta_group::2 MMA seems to cost >= ~100 cycles whatever its width,
+            // so three N = 128 pair MMAs per k-step ran 40-50 % slower than the widened two of the single-CTA kernel
+            // (deconv3 1627 -> 2452 us); at N = 256 the pair wins (conv4 499 -> 438 us).  P2P_PAIR_BN128=1 = experiment.
+            static const int pair_min_bn = getenv("P2P_PAIR_BN128") && atoi(getenv("P2P_PAIR_BN128")) ? 128 : 256;
+            const bool use_pair = persistent && pair && c.BN >= pair_min_bn && c.splitk <= 1 && c.kind != K_DENSE && c.act != ACT_HEADS &&
+                                  c.res_tensor < 0 && rt.has_out && tma_store && grid.x >= 2;
+            if (use_pair) {
+                p.tma_store = 1;
+                p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
+                const int pairs = static_cast<int>((grid.x + 1) / 2 * grid.y * grid.z);
+                if (c.BN == 256) {
+                    if (np == 2) launch_conv_pair<256, 2>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
+                    else launch_conv_pair<256, 1>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
+                } else {
+                    if (np == 2) launch_conv_pair<128, 2>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
+                    else launch_conv_pair<128, 1>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
+                }
+            } else if (persistent) {
                 p.tma_store = (tma_store && rt.has_out) ? 1 : 0;
                 {
                     // epilogue-bound layers (few k-iterations per tile) run on fewer operand stages and use the freed

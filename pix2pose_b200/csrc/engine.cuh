@@ -72,6 +72,7 @@ struct ModelConv {
     DevBuf<__half> packed;  // [KI][NP][Cout_pad][64]
     DevBuf<float> scale, shift;
     CUtensorMap mapB;
+    CUtensorMap mapBh;   // same weights, box of BN / 2 rows: each CTA of a pair loads one half (conv_tc_pair.cuh)
 };
 
 class Engine;
@@ -102,6 +103,7 @@ class Engine {
     int single_acc_steps = 40;  // accumulation chains up to this many k16 steps use one TMEM accumulator (P2P_SINGLE_ACC_STEPS)
     bool res_tma = true;      // residual tiles by TMA into shared memory (P2P_RES_TMA=0 = per-thread loads)
     bool tma_store = true;    // TMA-store epilogue in the persistent kernel (default; P2P_TMA_STORE=0 = direct 16-byte stores)
+    bool pair = true;         // CTA-pair kernel (cta_group::2, M = 256) for the wide decoder convs (P2P_PAIR=0 disables)
     bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
 
     // x_dev -> dec_dev / prob_dev for n <= cap crops; n_active (device int) optionally limits work further.

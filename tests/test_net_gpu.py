@@ -58,7 +58,7 @@ def test_batch_edges_and_chunking(inputs):
     """n = 0, n = 1, n > capacity (chunked), batch invariance (a crop's output does not depend on its batch)."""
     from pix2pose_b200 import ae_model
     w = W.synthetic_weights("paper", 1)
-    m = ae_model.GeneratorModel("paper", capacity=2, precision="fp16x3")
+    m = ae_model.GeneratorModel("paper", engine=ae_model.Engine("paper", 2, "fp16x3"))   # not the shared (larger) engine
     m.load_weights(w)
     d0, p0 = m.predict(np.zeros((0, 128, 128, 3), np.float32))
     assert d0.shape == (0, 128, 128, 3) and p0.shape == (0, 128, 128, 1)
@@ -66,6 +66,11 @@ def test_batch_edges_and_chunking(inputs):
     for i in (0, 4):
         d1, p1 = m.predict(inputs[i:i + 1])
         assert np.array_equal(d1[0], d5[i]) and np.array_equal(p1[0], p5[i])
+    # the same through one batch of 5 (kernel variants are chosen per layer by the tile count: single-CTA / CTA-pair)
+    big = ae_model.GeneratorModel("paper", engine=ae_model.Engine("paper", 8, "fp16x3"))
+    big.load_weights(w)
+    d8, p8 = big.predict(inputs)
+    assert np.array_equal(d8, d5) and np.array_equal(p8, p5)
     with pytest.raises(ValueError):
         m.predict(np.zeros((1, 64, 64, 3), np.float32))
 
