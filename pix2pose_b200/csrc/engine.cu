@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "conv_tc_pair.cuh"
+#include "conv_tc_slab.cuh"
 #include "net_kernels.cuh"
 
 namespace p2p {
@@ -332,6 +333,25 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
     c.tw = std::min(c.W, 16);
     c.th = std::min(c.H, 128 / c.tw);
     c.nb = 128 / (c.tw * c.th);
+    // slab-reuse kernel (conv_tc_slab.cuh): 8 x 16 pixel tiles, one entry per (source, 64-channel chunk)
+    c.slab = false;
+    c.slabs.clear();
+    static const bool slab_on = !getenv("P2P_SLAB") || atoi(getenv("P2P_SLAB")) != 0;
+    if (slab_on && c.kind == K_CONV && c.ksize >= 3 && c.ksize <= 5 && c.BN == 128 && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() <= 2 &&
+        c.res_tensor < 0 && c.splitk <= 1) {
+        c.slab = true;
+        c.tw = 8; c.th = 16; c.nb = 1;
+        int src_base = 0;
+        for (size_t si = 0; si < c.srcs.size(); ++si) {
+            const SrcSpec& sp = c.srcs[si];
+            const int nch = chunks(sp.c_count);
+            for (int ch = 0; ch < nch; ++ch) {
+                const int nvalid = std::min(64, sp.c_count - ch * 64);
+                c.slabs.push_back(make_int4(static_cast<int>(si) | (((nvalid + 15) / 16) << 8), sp.c_begin + ch * 64, src_base + ch, nch));
+            }
+            src_base += c.ksize * c.ksize * nch;
+        }
+    }
 }
 
 }  // namespace
@@ -460,6 +480,8 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
     if (const char* e = getenv("P2P_PAIR")) pair = atoi(e) != 0;
+    if (const char* e = getenv("P2P_SLAB")) slab = atoi(e) != 0;
+    if (const char* e = getenv("P2P_SLAB_CLUSTER")) slab_cluster = atoi(e);
     if (const char* e = getenv("P2P_TMA_STORE")) tma_store = atoi(e) != 0;
     if (const char* e = getenv("P2P_SINGLE_ACC_STEPS")) single_acc_steps = atoi(e);
     if (const char* e = getenv("P2P_EPI_NK")) epi_nk = atoi(e);
@@ -564,6 +586,21 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 encode(&rt.mapRes, tensors[c.res_tensor].buf.p, 5, dims, str, box);
                 rt.has_res = true;
             }
+        }
+        memset(rt.mapSlab, 0, sizeof(rt.mapSlab));
+        if (c.slab) {
+            rt.slabs.upload(c.slabs.data(), c.slabs.size());
+            const int pad = (c.ksize - 1) / 2;
+            for (size_t si = 0; si < c.srcs.size(); ++si) {
+                const SrcSpec& sp = c.srcs[si];
+                const TensorSpec& t = plan.tensors[sp.tensor];
+                const cuuint64_t C = t.C, W = t.W, H = t.H;
+                cuuint64_t dims[5] = {(cuuint64_t)(sp.c_begin + sp.c_count), W, H, (cuuint64_t)cap, (cuuint64_t)np};
+                cuuint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, static_cast<cuuint64_t>(cap) * H * W * C * 2};
+                cuuint32_t box[5] = {64, 8, (cuuint32_t)(16 + 2 * pad), 1, (cuuint32_t)np};
+                encode(&rt.mapSlab[si], tensors[sp.tensor].buf.p, 5, dims, str, box);
+            }
+            if (c.srcs.size() < 2) rt.mapSlab[1] = rt.mapSlab[0];
         }
     }
     P2P_CUDA(cudaDeviceSynchronize());
@@ -716,6 +753,12 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
         cuuint64_t str[3] = {128, (cuuint64_t)c.Cout_pad * 128, (cuuint64_t)c.Cout_pad * 128 * np};
         cuuint32_t box[4] = {64, (cuuint32_t)c.BN, (cuuint32_t)np, 1};
         encode(&mc.mapB, mc.packed.p, 4, dims, str, box);
+        mc.mapBmc[0] = mc.mapBmc[1] = mc.mapB;
+        if (c.BN == 128) {
+            cuuint32_t b2[4] = {64, 64, 1, 1}, b4[4] = {64, 32, 1, 1};
+            encode(&mc.mapBmc[0], mc.packed.p, 4, dims, str, b2);
+            encode(&mc.mapBmc[1], mc.packed.p, 4, dims, str, b4);
+        }
         if (c.BN >= 128) {
             cuuint32_t boxh[4] = {64, (cuuint32_t)(c.BN / 2), (cuuint32_t)np, 1};
             encode(&mc.mapBh, mc.packed.p, 4, dims, str, boxh);
@@ -741,6 +784,30 @@ void launch_conv_persistent(const CUtensorMap* mA, const CUtensorMap& mB, const 
     }
     conv_tc_persistent_kernel<BN, NP><<<ctas, 64 + kEpiThreads, Cfg::SMEM_BYTES_P, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO[0], mO[1], mO[2], mO[3], mR, p);
     P2P_CUDA(cudaGetLastError());
+}
+
+template <int BN, int NP, int CL>
+void launch_conv_slab(const CUtensorMap* mS, const CUtensorMap& mB, const CUtensorMap& mO, const ConvParams& p, int tiles, int num_sms,
+                      cudaStream_t s) {
+    using SC = SlabCfg<BN, NP>;
+    static bool configured = false;
+    if (!configured) {
+        P2P_CUDA(cudaFuncSetAttribute(conv_tc_slab_kernel<BN, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES));
+        configured = true;
+    }
+    const int groups = std::min((tiles + CL - 1) / CL, num_sms / CL);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(groups * CL, 1, 1);
+    cfg.blockDim = dim3(64 + kEpiThreads, 1, 1);
+    cfg.dynamicSmemBytes = SC::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    P2P_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<BN, NP, CL>, mS[0], mS[1], mB, mO, p));
 }
 
 // CTA-pair kernel: grid = 2 x (clusters that can be resident at once, at most one per tile pair)
@@ -883,7 +950,26 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             static const int pair_min_bn = getenv("P2P_PAIR_BN128") && atoi(getenv("P2P_PAIR_BN128")) ? 128 : 256;
             const bool use_pair = persistent && pair && c.BN >= pair_min_bn && c.splitk <= 1 && c.kind != K_DENSE && c.act != ACT_HEADS &&
                                   c.res_tensor < 0 && rt.has_out && tma_store && grid.x >= 2;
-            if (use_pair) {
+            if (persistent && slab && c.slab && rt.has_out && tma_store) {
+                p.tma_store = 1;
+                p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
+                p.slab_ksize = c.ksize;
+                p.kit = rt.slabs.p;
+                p.kstart[0] = 0;
+                for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
+                for (size_t i = 0; i < c.slabs.size(); ++i) p.ksteps_tab[i] = static_cast<uint8_t>(c.slabs[i].x >> 8);
+                const int tiles = static_cast<int>(grid.x * grid.y);
+                const int cl = tiles >= 2 * num_sms ? slab_cluster : 1;  // small launches: no point in pairing up CTAs
+                if (np == 2) {
+                    if (cl == 4) launch_conv_slab<128, 2, 4>(rt.mapSlab, mc.mapBmc[1], rt.mapOut[0], p, tiles, num_sms, s);
+                    else if (cl == 2) launch_conv_slab<128, 2, 2>(rt.mapSlab, mc.mapBmc[0], rt.mapOut[0], p, tiles, num_sms, s);
+                    else launch_conv_slab<128, 2, 1>(rt.mapSlab, mc.mapB, rt.mapOut[0], p, tiles, num_sms, s);
+                } else {
+                    if (cl == 4) launch_conv_slab<128, 1, 4>(rt.mapSlab, mc.mapBmc[1], rt.mapOut[0], p, tiles, num_sms, s);
+                    else if (cl == 2) launch_conv_slab<128, 1, 2>(rt.mapSlab, mc.mapBmc[0], rt.mapOut[0], p, tiles, num_sms, s);
+                    else launch_conv_slab<128, 1, 1>(rt.mapSlab, mc.mapB, rt.mapOut[0], p, tiles, num_sms, s);
+                }
+            } else if (use_pair) {
                 p.tma_store = 1;
                 p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
                 const int pairs = static_cast<int>((grid.x + 1) / 2 * grid.y * grid.z);

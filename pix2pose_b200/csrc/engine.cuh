@@ -51,6 +51,8 @@ struct ConvSpec {
     std::vector<KWeight> kw;
     struct MapReq { int tensor, view, climit; };  // view: 0 normal, 1..4 parity (py*2+px+1), 5 dense
     std::vector<MapReq> maps;
+    bool slab = false;                 // runs on conv_tc_slab_kernel (k x k stride-1 conv, Cout 128, W % 8 == 0, H % 16 == 0)
+    std::vector<int4> slabs;           // slab kernel: one entry per (source, 64-channel chunk)
 };
 
 struct TensorSpec { std::string name; int H, W, C; };
@@ -72,6 +74,7 @@ struct ModelConv {
     DevBuf<__half> packed;  // [KI][NP][Cout_pad][64]
     DevBuf<float> scale, shift;
     CUtensorMap mapB;
+    CUtensorMap mapBmc[2];  // BN = 128 convs: one-plane boxes of 64 / 32 rows for the 2- / 4-CTA weight multicast (conv_tc_slab.cuh)
     CUtensorMap mapBh;   // same weights, box of BN / 2 rows: each CTA of a pair loads one half (conv_tc_pair.cuh)
 };
 
@@ -95,7 +98,7 @@ class Engine {
     std::vector<Tensor> tensors;
     DevBuf<float> x, dec, prob;  // (cap,128,128,3), (cap,128,128,3), (cap,128,128)
     DevBuf<float> partial;       // split-K scratch [slices][cap][Cout_pad]
-    struct ConvRt { DevBuf<int4> kit; CUtensorMap mapA[4]; CUtensorMap mapOut[4]; bool has_out = false; CUtensorMap mapRes; bool has_res = false; };
+    struct ConvRt { DevBuf<int4> kit, slabs; CUtensorMap mapA[4]; CUtensorMap mapSlab[2]; CUtensorMap mapOut[4]; bool has_out = false; CUtensorMap mapRes; bool has_res = false; };
     std::vector<ConvRt> conv_rt;
     int num_sms = 148;
     bool prof_layers = false; // print per-launch times in profile mode (P2P_PROF_LAYERS)
@@ -103,6 +106,9 @@ class Engine {
     int single_acc_steps = 40;  // accumulation chains up to this many k16 steps use one TMEM accumulator (P2P_SINGLE_ACC_STEPS)
     bool res_tma = true;      // residual tiles by TMA into shared memory (P2P_RES_TMA=0 = per-thread loads)
     bool tma_store = true;    // TMA-store epilogue in the persistent kernel (default; P2P_TMA_STORE=0 = direct 16-byte stores)
+    int slab_cluster = 1;     // CTAs sharing every weight stage by TMA multicast in the slab kernel (P2P_SLAB_CLUSTER=1|2|4; measured:
+                              // 2 gains 1 %, 4 loses 75 % to cluster placement -- the layer is bound by shared-memory bandwidth, not by L2)
+    bool slab = true;         // slab-reuse kernel for the Cout-128 k x k convs (P2P_SLAB=0 disables)
     bool pair = true;         // CTA-pair kernel (cta_group::2, M = 256) for the wide decoder convs (P2P_PAIR=0 disables)
     bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
 

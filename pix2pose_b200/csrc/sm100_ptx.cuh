@@ -189,6 +189,21 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                  : "memory");
 }
 
+// ---------------------------------------------------------------- cluster multicast (one-CTA MMAs, shared operand tiles)
+// TMA load whose box is written to the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's
+// mbarrier (same offset) receives the transaction bytes.
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrives on the mbarrier at the same offset in every CTA of `cta_mask` once this thread's one-CTA MMAs completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B (64 fp16), 8-row
 // groups 1024 B apart (SBO), tile base 1024-B aligned.  Advancing along K inside the swizzle
 // atom = adding the byte offset to the start address.
