@@ -82,6 +82,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def conv_traffic(capacity):
+    """DRAM bytes (read + write) of the conv_tc launches of ONE forward of `capacity` crops, from the committed ncu capture
+    (profiles/conv_traffic.json, written from scripts/ncu_step_metrics.py output); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if int(d.get("capacity", -1)) == int(capacity):
+            return float(d["dram_bytes_per_forward"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,7 +266,7 @@ def run_ours(args):
         "e2e": {"value": n_total / (ms_e2e / args.steps * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": conv_traffic(args.capacity), "peak_source": peak_src,
                      "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one %d-crop forward: %.3f ms; other kernels %.3f ms)" % (
                          cnt[0], args.capacity, msk[0], msk[1]),
                      "note": "algorithmic FLOPs (10.70 GFLOP/crop); fp16x3 issues 3 MMAs per k-step, so tensor-pipe work is 3x this"},

@@ -237,7 +237,7 @@ __global__ void cand_scan_kernel(DetState* __restrict__ state, CandStats* __rest
 // P4: stage-2 post-processing per candidate (recognition.py:132-154, :196-213)
 constexpr int kPostThreads = 512;
 
-__global__ void __launch_bounds__(kPostThreads) stage2_post_kernel(const DetIn* __restrict__ dets, const DetState* __restrict__ state,
+__global__ void __launch_bounds__(kPostThreads, 2) stage2_post_kernel(const DetIn* __restrict__ dets, const DetState* __restrict__ state,
                                                                    CandStats* __restrict__ cands, const int* __restrict__ n_total,
                                                                    const float* __restrict__ dec2, const float* __restrict__ prob2,
                                                                    int n_th, double th_i, uint8_t* __restrict__ xyz_u8,
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kPostThreads) stage2_post_kernel(const DetIn* 
         return;
     }
     __shared__ float s_pmin, s_pmax, s_imin, s_imax;
-    __shared__ int s_ng128, s_warp[kPostThreads / 32], s_base, s_nng;
+    __shared__ int s_ng128, s_base, s_nng;
     __shared__ long long s_sv, s_su;
     CandStats& cs = cands[c];
     const int d = cs.det, k = cs.k;
@@ -308,68 +308,113 @@ __global__ void __launch_bounds__(kPostThreads) stage2_post_kernel(const DetIn* 
     const int npx = (h > 0 && w > 0) ? h * w : 0;
     int nng = 0;
     long long sv = 0, su = 0;
-    for (int base = 0; base < npx; base += blockDim.x) {
-        const int q = base + threadIdx.x;
-        bool is_valid = false;
-        float o3[3] = {0, 0, 0};
-        int i = 0, j = 0;
-        if (q < npx) {
-            i = q / w; j = q - i * w;
-            const Lerp ly = axis_map(i + b[8], 128, side_v), lx = axis_map(j + b[10], 128, side_u);
-            const int ys[2] = {ly.lo, ly.hi}, xs[2] = {lx.lo, lx.hi};
-            double tp[2][2], tg[2][2], tx[2][2][3];
+    // Two passes per super-chunk of kMaxChunks x 512 pixels instead of three block barriers per 512-pixel chunk:
+    //   B1  every thread resizes / quantises its pixels, writes the uint8 map and the valid mask, and each warp leaves
+    //       its per-chunk count of valid pixels in shared memory;
+    //   --  one block-wide exclusive scan over the chunk totals;
+    //   B2  every thread re-reads its own valid flags / uint8 values (its own writes, no fence needed) and writes the
+    //       correspondences at offset (pixels before this super-chunk) + (chunks before) + (warps before) + (lanes before):
+    //       the row-major order np.where produces (:205-211).
+    constexpr int kMaxChunks = 1024, kWarps = kPostThreads / 32;
+    __shared__ uint8_t s_cnt[kMaxChunks * kWarps];
+    __shared__ int s_coff[kMaxChunks];
+    __shared__ int s_wtot[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sbase = 0; sbase < npx; sbase += kMaxChunks * kPostThreads) {
+        const int nch = min(kMaxChunks, (npx - sbase + kPostThreads - 1) / kPostThreads);
+        // ---- B1
+        for (int c = 0; c < nch; ++c) {
+            const int q = sbase + c * kPostThreads + threadIdx.x;
+            bool is_valid = false;
+            int i = 0, j = 0;
+            if (q < npx) {
+                i = q / w; j = q - i * w;
+                const Lerp ly = axis_map(i + b[8], 128, side_v), lx = axis_map(j + b[10], 128, side_u);
+                const int ys[2] = {ly.lo, ly.hi}, xs[2] = {lx.lo, lx.hi};
+                double tp[2][2], tg[2][2], tx[2][2][3];
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int y = ys[a], x = xs[e];
-                    if (y < 0 || y >= 128 || x < 0 || x >= 128) {
-                        tp[a][e] = 1.0; tg[a][e] = 0.0; tx[a][e][0] = tx[a][e][1] = tx[a][e][2] = 0.5;  // cval 1 / 0 / 0.5
-                    } else {
-                        const int p = y * 128 + x;
-                        const float vx = dc[p * 3], vy = dc[p * 3 + 1], vz = dc[p * 3 + 2];
-                        const bool gray = norm3_f32(vx, vy, vz) < 0.3f;
-                        tp[a][e] = pb[p];
-                        tg[a][e] = gray ? 0.0 : 1.0;
-                        const float v3[3] = {vx, vy, vz};
+                    for (int e = 0; e < 2; ++e) {
+                        const int y = ys[a], x = xs[e];
+                        if (y < 0 || y >= 128 || x < 0 || x >= 128) {
+                            tp[a][e] = 1.0; tg[a][e] = 0.0; tx[a][e][0] = tx[a][e][1] = tx[a][e][2] = 0.5;  // cval 1 / 0 / 0.5
+                        } else {
+                            const int p = y * 128 + x;
+                            const float vx = dc[p * 3], vy = dc[p * 3 + 1], vz = dc[p * 3 + 2];
+                            const bool gray = norm3_f32(vx, vy, vz) < 0.3f;
+                            tp[a][e] = pb[p];
+                            tg[a][e] = gray ? 0.0 : 1.0;
+                            const float v3[3] = {vx, vy, vz};
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            float ip = __fdiv_rn(__fadd_rn(gray ? 0.f : v3[ch], 1.f), 2.f);
-                            tx[a][e][ch] = fminf(fmaxf(ip, 0.f), 1.f);
+                            for (int ch = 0; ch < 3; ++ch) {
+                                float ip = __fdiv_rn(__fadd_rn(gray ? 0.f : v3[ch], 1.f), 2.f);
+                                tx[a][e][ch] = fminf(fmaxf(ip, 0.f), 1.f);
+                            }
                         }
                     }
-                }
-            const double prob_ori = clip_keep(bilerp(tp[0][0], tp[0][1], tp[1][0], tp[1][1], ly.w, lx.w), pmin, pmax, 1.0);  // :134
-            const bool ng = clip_keep(bilerp(tg[0][0], tg[0][1], tg[1][0], tg[1][1], ly.w, lx.w), gmin, gmax, 0.0) > 0.9;   // :146
-            uint8_t u8[3];
+                const double prob_ori = clip_keep(bilerp(tp[0][0], tp[0][1], tp[1][0], tp[1][1], ly.w, lx.w), pmin, pmax, 1.0);  // :134
+                const bool ng = clip_keep(bilerp(tg[0][0], tg[0][1], tg[1][0], tg[1][1], ly.w, lx.w), gmin, gmax, 0.0) > 0.9;   // :146
+                uint8_t u8[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const double v = clip_keep(bilerp(tx[0][0][ch], tx[0][1][ch], tx[1][0][ch], tx[1][1][ch], ly.w, lx.w), imin, imax, 0.5) * 255;  // :144
-                u8[ch] = static_cast<uint8_t>(static_cast<int>(v));  // :154 float -> uint8 truncation
-                xyz_u8[(pool + q) * 3 + ch] = u8[ch];
-                o3[ch] = static_cast<float>((static_cast<double>(u8[ch]) / 255 * 2 - 1) * det.scale[ch] + det.ct[ch]);  // :198-202
+                for (int ch = 0; ch < 3; ++ch) {
+                    const double v = clip_keep(bilerp(tx[0][0][ch], tx[0][1][ch], tx[1][0][ch], tx[1][1][ch], ly.w, lx.w), imin, imax, 0.5) * 255;  // :144
+                    u8[ch] = static_cast<uint8_t>(static_cast<int>(v));  // :154 float -> uint8 truncation
+                    xyz_u8[(pool + q) * 3 + ch] = u8[ch];
+                }
+                if (ng) { ++nng; sv += i + b[4]; su += j + b[6]; }
+                is_valid = ng && prob_ori < th_i;  // :203-204
+                valid[pool + q] = is_valid ? 1 : 0;
             }
-            if (ng) { ++nng; sv += i + b[4]; su += j + b[6]; }
-            is_valid = ng && prob_ori < th_i;  // :203-204
-            valid[pool + q] = is_valid ? 1 : 0;
+            const unsigned ball = __ballot_sync(0xffffffffu, is_valid);
+            if (lane == 0) s_cnt[c * kWarps + warp] = static_cast<uint8_t>(__popc(ball));
         }
-        // ordered (row-major) compaction of the valid pixels of this chunk
-        const unsigned ball = __ballot_sync(0xffffffffu, is_valid);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) s_warp[warp] = __popc(ball);
         __syncthreads();
-        int before = s_base;
-        for (int wv = 0; wv < warp; ++wv) before += s_warp[wv];
-        if (is_valid) {
-            const long long dst = pool + before + __popc(ball & ((1u << lane) - 1));
-            obj[dst * 3] = o3[0]; obj[dst * 3 + 1] = o3[1]; obj[dst * 3 + 2] = o3[2];
-            img[dst * 2] = static_cast<float>(j + b[6]);      // u + u1  (:209-211)
-            img[dst * 2 + 1] = static_cast<float>(i + b[4]);  // v + v1
+        // ---- exclusive scan of the chunk totals (thread t owns chunks 2t, 2t + 1)
+        {
+            int t0 = 0, t1 = 0;
+            const int c0 = 2 * threadIdx.x, c1 = c0 + 1;
+            if (c0 < nch)
+                for (int wv = 0; wv < kWarps; ++wv) t0 += s_cnt[c0 * kWarps + wv];
+            if (c1 < nch)
+                for (int wv = 0; wv < kWarps; ++wv) t1 += s_cnt[c1 * kWarps + wv];
+            const int pair = t0 + t1;
+            int incl = pair;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_wtot[warp] = incl;
+            __syncthreads();
+            int before = 0;
+            for (int wv = 0; wv < warp; ++wv) before += s_wtot[wv];
+            const int excl = before + incl - pair;
+            if (c0 < nch) s_coff[c0] = excl;
+            if (c1 < nch) s_coff[c1] = excl + t0;
+            __syncthreads();
+        }
+        // ---- B2
+        for (int c = 0; c < nch; ++c) {
+            const int q = sbase + c * kPostThreads + threadIdx.x;
+            const bool is_valid = q < npx && valid[pool + q] != 0;
+            const unsigned ball = __ballot_sync(0xffffffffu, is_valid);
+            if (is_valid) {
+                int before = s_base + s_coff[c];
+                for (int wv = 0; wv < warp; ++wv) before += s_cnt[c * kWarps + wv];
+                const long long dst = pool + before + __popc(ball & ((1u << lane) - 1));
+                const int i = q / w, j = q - i * w;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    obj[dst * 3 + ch] = static_cast<float>((static_cast<double>(xyz_u8[(pool + q) * 3 + ch]) / 255 * 2 - 1) * det.scale[ch] + det.ct[ch]);  // :198-202
+                img[dst * 2] = static_cast<float>(j + b[6]);      // u + u1  (:209-211)
+                img[dst * 2 + 1] = static_cast<float>(i + b[4]);  // v + v1
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
-            for (int wv = 0; wv < kPostThreads / 32; ++wv) tot += s_warp[wv];
+            for (int wv = 0; wv < kWarps; ++wv) tot += s_wtot[wv];
             s_base += tot;
         }
         __syncthreads();
