@@ -128,6 +128,9 @@ P2P_API int p2p_pipeline_fetch_decode(p2p_pipeline_t* p, int stage, int index, f
 P2P_API int p2p_pipeline_fetch_buffer(p2p_pipeline_t* p, int what, int index, float* out);
 /* Test hook: the NEXT run replaces the network outputs of `stage` (1|2) by these host arrays (planted-pose parity tests). */
 P2P_API int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decode, const float* prob, int n);
+/* box_size of pix2pose.__init__ (recognition.py:10, :19; used by get_boxes :33-34 for the stage-1 box and for the
+ * refined boxes :110).  Applies to the following runs; default 1.5. */
+P2P_API int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size);
 P2P_API long long p2p_pipeline_launch_count(const p2p_pipeline_t* p);
 
 /* Measurement helper: uploads x (n <= capacity crops, host), then times `iters` device-resident

@@ -156,6 +156,13 @@ int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decod
         p->p->set_override(stage, decode, prob, n);
     });
 }
+int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        P2P_CHECK(box_size > 0.0 && box_size < 100.0, "box_size %g outside (0, 100)", box_size);
+        p->p->box_size = box_size;
+    });
+}
 long long p2p_pipeline_launch_count(const p2p_pipeline_t* p) { return p ? p->p->launches + p->p->pnp.launches : 0; }
 
 int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,

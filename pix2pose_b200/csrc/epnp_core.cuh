@@ -34,7 +34,10 @@ P2P_HD inline double dist2(const double* a, const double* b) {
 // tred2 / tqli pair): ~10x fewer operations than cyclic Jacobi for N = 12, which matters because the RANSAC
 // kernel runs one of these per hypothesis per thread.  Same contract as jacobi_eig_sym: `A` (row-major) is
 // destroyed, w descending, row i of `Vt` = unit eigenvector of w[i].
-template <int N>
+// FIRST > 0 keeps only the eigenvectors FIRST .. N-1 (the smallest eigenvalues): row i of the full Vt lands in row
+// i - FIRST of `Vt` ((N - FIRST) x N).  EPnP only ever reads the last four, and the RANSAC kernel is bound by the
+// per-thread local-memory footprint, so the 5-point solver does not materialise the other eight.
+template <int N, int FIRST = 0>
 P2P_HD inline void tridiag_eig_sym(double* A, double* Vt, double* w) {
     double d[N], e[N];
     // ---- tred2: A -> tridiagonal (d, e), A overwritten by the orthogonal transformation Q
@@ -149,7 +152,8 @@ P2P_HD inline void tridiag_eig_sym(double* A, double* Vt, double* w) {
     }
     for (int i = 0; i < N; ++i) {
         w[i] = d[order[i]];
-        for (int k = 0; k < N; ++k) Vt[i * N + k] = A[k * N + order[i]];
+        if (i >= FIRST)
+            for (int k = 0; k < N; ++k) Vt[(i - FIRST) * N + k] = A[k * N + order[i]];
     }
 }
 
@@ -433,8 +437,9 @@ P2P_HD inline void m_rows(const double* a, double u, double v, const Cam& cam, d
     }
 }
 
-P2P_HD inline void compute_L_6x10(const double* ut, double* l) {
-    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+// ut8 = rows 8..11 of the 12 x 12 eigenvector matrix (4 x 12): the null-space candidates, smallest eigenvalue last
+P2P_HD inline void compute_L_6x10(const double* ut8, double* l) {
+    const double* v[4] = {ut8 + 12 * 3, ut8 + 12 * 2, ut8 + 12 * 1, ut8};
     double dv[4][6][3];
     for (int i = 0; i < 4; ++i) {
         int a = 0, b = 1;
@@ -515,22 +520,22 @@ P2P_HD inline void gauss_newton(const double* l, const double* rho, double* beta
     }
 }
 
-// From the 12x12 M^T M: eigenvectors (rows of ut, descending eigenvalues) and the three refined
+// From the 12x12 M^T M: the four eigenvectors of the smallest eigenvalues (rows of ut8) and the three refined
 // beta sets (epnp.cpp compute_pose, middle part).
-P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut, double betas[3][4]) {
+P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
     double w[12], l[60], rho[6];
-    tridiag_eig_sym<12>(mtm, ut, w);
-    compute_L_6x10(ut, l);
+    tridiag_eig_sym<12, 8>(mtm, ut8, w);
+    compute_L_6x10(ut8, l);
     compute_rho(cws, rho);
     find_betas_approx_1(l, rho, betas[0]); gauss_newton(l, rho, betas[0]);
     find_betas_approx_2(l, rho, betas[1]); gauss_newton(l, rho, betas[1]);
     find_betas_approx_3(l, rho, betas[2]); gauss_newton(l, rho, betas[2]);
 }
 
-P2P_HD inline void compute_ccs(const double* betas, const double* ut, double ccs[4][3]) {
+P2P_HD inline void compute_ccs(const double* betas, const double* ut8, double ccs[4][3]) {
     for (int i = 0; i < 4; ++i) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
     for (int i = 0; i < 4; ++i) {
-        const double* v = ut + 12 * (11 - i);
+        const double* v = ut8 + 12 * (3 - i);
         for (int j = 0; j < 4; ++j)
             for (int k = 0; k < 3; ++k) ccs[j][k] += betas[i] * v[3 * j + k];
     }
@@ -645,7 +650,7 @@ P2P_HD inline void solve_small(const double* pws, const double* us, int n, const
         for (int a = 0; a < 12; ++a)
             for (int b = 0; b < 12; ++b) mtm[a * 12 + b] += m1[a] * m1[b] + m2[a] * m2[b];
     }
-    double ut[144], betas[3][4];
+    double ut[48], betas[3][4];   // eigenvectors 8..11 only
     solve_betas(mtm, cws, ut, betas);
     double best = 0;
     for (int k = 0; k < 3; ++k) {

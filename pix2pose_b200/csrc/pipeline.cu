@@ -552,7 +552,7 @@ void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, 
         P2P_CUDA(cudaStreamSynchronize(s));
         ov_dec_[0].clear(); ov_prob_[0].clear();
     }
-    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, th_.p, n_th, H, W, 1.5);
+    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, th_.p, n_th, H, W, box_size);
     P2P_CUDA(cudaGetLastError());
     const int C = n * n_th;
     const int n_chunks = (C + cap - 1) / cap;

@@ -85,6 +85,7 @@ class Pipeline {
     // Host frames (F,H,W,3) uint8 -> device copy owned by the pipeline.
     const uint8_t* upload_frames(const uint8_t* frames_host, int F, int H, int W);
     long long launches = 0;
+    double box_size = 1.5;   // recognition.py:19 (refined boxes, :110)
     Engine* engine;
     PnpSolver pnp;
     int max_dets, n_th;

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         block_reduce<52>(v, s_red, s_sum);
     }
     if (threadIdx.x == 0) {
-        double mtm[144], ut[144], betas[3][4];
+        double mtm[144], ut[48], betas[3][4];
         int k = 0;
         for (int x = 0; x < 4; ++x)
             for (int y = x; y < 4; ++y) {

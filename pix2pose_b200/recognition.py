@@ -131,9 +131,6 @@ class pix2pose():
         self.obj_ct = obj_param[3:]     # x,y,z
         self.box_size = box_size
         self.dist_coeff = dist_coeff    # stored, never used (distCoeffs=None, recognition.py:216)
-        if box_size != 1.5:
-            # the device-side refined-box arithmetic (csrc/pipeline.cu stage1_post_kernel) fixes the default
-            raise ValueError("box_size other than the reference default 1.5 is not supported")
         if backbone == 'paper':
             self.generator_train = ae_model.aemodel_unet_prob(p=1.0, precision=precision, capacity=capacity)
         elif backbone == 'resnet50':
@@ -168,6 +165,7 @@ class pix2pose():
             ent = (h, want, eng)          # keeps the engine alive as long as the pipeline
             pix2pose._shared_pipes[key] = ent
         self._pipe = ent[0]
+        _lib.check(_lib.lib().p2p_pipeline_set_box_size(self._pipe, float(self.box_size)))   # pipelines are shared by objects
         return self._pipe
 
     def _release_pipe(self):

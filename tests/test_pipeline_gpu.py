@@ -61,6 +61,30 @@ def test_stagewise_bit_parity_with_same_network_outputs(rec, frame, roi):
         assert got[2].shape == (3, 3) and got[3].shape == (3,)
 
 
+def test_non_default_box_size_matches_oracle(frame):
+    """box_size is a constructor argument of the reference (recognition.py:10, :19); the device-side refined-box
+    arithmetic follows it (p2p_pipeline_set_box_size)."""
+    from oracle.recognition_oracle import Pix2PoseOracle
+    from pix2pose_b200.recognition import pix2pose
+    r = pix2pose(W.synthetic_weights("resnet50", 1), K_LM, 640, 480, OBJ, backbone="resnet50", capacity=16, max_dets=16, box_size=1.2, **TH)
+    ora = Pix2PoseOracle(r.generator_train, K_LM, 640, 480, OBJ, box_size=1.2, **TH)
+    ora.trace = {}
+    roi = np.array([150, 250, 290, 370])
+    want = ora.est_pose(frame, roi)
+    got = r.est_pose(frame, roi)
+    assert list(got[5]) == list(want[5])
+    assert np.array_equal(r.debug_fetch(3, 0), ora.trace["x1"].astype(np.float32))
+    for k in range(len(ora.trace["x2"])):
+        assert np.array_equal(r.debug_fetch(4, k), ora.trace["x2"][k].astype(np.float32)), k
+    for c in ora.trace["cands"]:
+        xyz, mask, _ = _cand_crop(r, c["cid"], c["box"])
+        assert np.array_equal(xyz, c["xyz_u8"]) and np.array_equal(mask, np.asarray(c["valid_mask"], bool)), c["cid"]
+    # and the default is restored for other objects sharing the pipeline
+    r2 = pix2pose(W.synthetic_weights("resnet50", 1), K_LM, 640, 480, OBJ, backbone="resnet50", capacity=16, max_dets=16, **TH)
+    ora2 = Pix2PoseOracle(r2.generator_train, K_LM, 640, 480, OBJ, **TH)
+    assert list(r2.est_pose(frame, roi)[5]) == list(ora2.est_pose(frame, roi)[5])
+
+
 def test_sentinel_returns(rec, frame):
     out = rec.est_pose(frame, np.array([200, 300, 203, 302]))          # crop < 5 px (recognition.py:78-79)
     assert out[0].shape == (1,) and out[1] == -1 and out[2] == -1 and out[3] == -1 and out[4] == -1
