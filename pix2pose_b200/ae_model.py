@@ -68,8 +68,9 @@ class GeneratorModel:
 
     # -- keras surface ---------------------------------------------------------------------------
     def load_weights(self, path_or_dict):
-        """``.npz`` written by ``weights.save_npz`` (or a dict of Keras-layout arrays).  Keras
-        ``.hdf5`` files are converted offline with ``tools/convert_keras_hdf5.py`` (needs h5py)."""
+        """A Keras weight file (``inference.hdf5`` / ``pix2pose.NN-x.hdf5``; recognition.py:23-26) read by the built-in
+        HDF5 reader (``weights.load_keras_hdf5``), an ``.npz`` written by ``weights.save_npz``, or a dict of
+        Keras-layout arrays."""
         if isinstance(path_or_dict, dict):
             w = path_or_dict
             W.check_shapes(w, self.backbone)
@@ -88,6 +89,16 @@ class GeneratorModel:
         self._release()
         self._model = h
         self.weights = w
+
+    def save_weights(self, path):
+        """Keras ``Model.save_weights`` counterpart (tools/4_convert_weights_inference.py:52): ``.hdf5`` / ``.h5`` in the
+        Keras layout, anything else as ``.npz``."""
+        if self.weights is None:
+            raise RuntimeError("save_weights() before load_weights()")
+        if str(path).endswith((".hdf5", ".h5")):
+            W.save_keras_hdf5(str(path), self.weights, self.backbone)
+        else:
+            W.save_npz(str(path), self.weights, self.backbone)
 
     def predict(self, x, batch_size=None, verbose=0):
         if self._model is None:

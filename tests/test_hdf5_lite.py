@@ -1,0 +1,114 @@
+"""Keras-HDF5 weight import without h5py: the built-in reader against files produced by the
+built-in writer (self-consistent pin: no libhdf5-written file exists in this sandbox), and the layer matching of
+``weights.keras_layers_to_weights`` against a file laid out the way Keras 2.2 writes the resnet50 generator
+(nested ResNet model in graph-depth order, auto-named decoder layers)."""
+import numpy as np
+import pytest
+
+from pix2pose_b200 import hdf5_lite, weights as W
+
+
+def test_reader_roundtrip_of_groups_datasets_attributes(tmp_path):
+    w = hdf5_lite.Writer()
+    a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    b = np.arange(5, dtype=np.int32)
+    w.create_dataset("g1/sub/a:0", a)
+    w.create_dataset("g1/b", b)
+    w.create_dataset("empty", np.zeros((0, 3), np.float32))
+    w.create_group("g2")
+    w.set_attr("", "layer_names", np.array([b"g1", b"g2"]))
+    w.set_attr("g1", "weight_names", np.array([b"sub/a:0", b"b"]))
+    w.set_attr("g1", "scale", np.float64(2.5))
+    p = str(tmp_path / "t.h5")
+    w.save(p)
+    with hdf5_lite.File(p) as f:
+        assert sorted(f.keys()) == ["empty", "g1", "g2"]
+        assert list(f.attrs["layer_names"]) == [b"g1", b"g2"]
+        assert list(f["g1"].attrs["weight_names"]) == [b"sub/a:0", b"b"] and f["g1"].attrs["scale"] == 2.5
+        assert np.array_equal(np.asarray(f["g1"]["sub/a:0"]), a) and f["g1/sub/a:0"].shape == (2, 3, 4)
+        assert np.array_equal(f["g1/b"][()], b) and f["g1/b"].dtype == np.int32
+        assert f["empty"][()].shape == (0, 3) and f["g2"].keys() == []
+        assert "g1" in f and "nope" not in f
+        with pytest.raises(KeyError):
+            f["g1/zzz"]
+
+
+def test_rejects_non_hdf5_and_names_unsupported_features(tmp_path):
+    p = tmp_path / "x.hdf5"
+    p.write_bytes(b"not an hdf5 file" * 10)
+    with pytest.raises(hdf5_lite.Hdf5Error):
+        hdf5_lite.File(str(p))
+
+
+def test_backbone_roundtrip_through_keras_layout(tmp_path):
+    w = W.synthetic_weights("paper", 3)
+    p = str(tmp_path / "inference.hdf5")
+    W.save_keras_hdf5(p, w, "paper")
+    got = W.load_keras_hdf5(p, "paper")
+    assert all(np.array_equal(w[k], got[k]) for k in W.param_names("paper"))
+
+
+def _keras_style_resnet50_file(path, w):
+    """The file Keras 2.2.1 writes for aemodel_unet_resnet50 (ae_model.py:175-240): layer_names in topological order,
+    the ResNet part as ONE nested model layer whose weight_names follow graph depth (branch2c and the shortcut conv
+    branch1 at the same depth, their BatchNorms after both), decoder layers auto-named."""
+    f = hdf5_lite.Writer()
+    table = W.layer_table("resnet50")
+    res = [t for t in table if t[0].startswith(("conv1", "bn_conv1", "res", "bn2", "bn3"))]
+    rest = [t for t in table if t not in res]
+    keys = lambda kind: ("gamma", "beta", "moving_mean", "moving_variance") if kind == W.BN else ("kernel", "bias")  # noqa: E731
+    # nested model: Keras depth order inside a conv_block = 2a, bn2a, 2b, bn2b, 2c, 1, bn2c, bn1
+    order = []
+    i = 0
+    while i < len(res):
+        name = res[i][0]
+        if name.endswith("branch2a") and i + 7 < len(res) and res[i + 6][0].endswith("branch1"):
+            blk = res[i:i + 8]       # 2a bn2a 2b bn2b 2c bn2c 1 bn1 (our table order)
+            order += [blk[0], blk[1], blk[2], blk[3], blk[4], blk[6], blk[5], blk[7]]
+            i += 8
+        else:
+            order.append(res[i])
+            i += 1
+    wn = []
+    for name, kind, _ in order:
+        for k in keys(kind):
+            f.create_dataset("model_1/%s/%s:0" % (name, k), w[name + "/" + k])
+            wn.append(("%s/%s:0" % (name, k)).encode())
+    f.set_attr("model_1", "weight_names", np.array(wn))
+    layer_names = [b"input_1", b"model_1", b"lambda_1"]
+    f.create_group("input_1")
+    f.set_attr("input_1", "weight_names", np.zeros((0,), "S1"))
+    f.create_group("lambda_1")
+    f.set_attr("lambda_1", "weight_names", np.zeros((0,), "S1"))
+    # encoder tail + decoder: conv4_1, conv4_2 keep their names, twin BNs follow both convs (same graph depth)
+    cnt = {W.BN: 0, W.DENSE: 0, W.CONV: 0, W.CONVT: 0}
+    auto = {W.BN: "batch_normalization_%d", W.DENSE: "dense_%d", W.CONV: "conv2d_%d", W.CONVT: "conv2d_transpose_%d"}
+    seq = [t for t in rest]
+    seq = [seq[0], seq[2], seq[1], seq[3]] + seq[4:]      # conv4_1, conv4_2, bn, bn
+    for name, kind, _ in seq:
+        if name in ("conv4_1", "conv4_2"):
+            kname = name
+        else:
+            cnt[kind] += 1
+            kname = auto[kind] % cnt[kind]
+        wn = []
+        for k in keys(kind):
+            f.create_dataset("%s/%s/%s:0" % (kname, kname, k), w[name + "/" + k])
+            wn.append(("%s/%s:0" % (kname, k)).encode())
+        f.set_attr(kname, "weight_names", np.array(wn))
+        layer_names.append(kname.encode())
+    f.set_attr("", "layer_names", np.array(layer_names))
+    f.save(path)
+
+
+def test_keras_style_resnet50_file_maps_onto_the_layer_table(tmp_path):
+    w = W.synthetic_weights("resnet50", 2)
+    p = str(tmp_path / "inference_resnet.hdf5")
+    _keras_style_resnet50_file(p, w)
+    got = W.load_keras_hdf5(p, "resnet50")
+    bad = [k for k in W.param_names("resnet50") if not np.array_equal(w[k], got[k])]
+    assert not bad, bad[:5]
+    # the same through the full-model wrapper group (ModelCheckpoint files: tools/3_train_pix2pose.py:273-276)
+    with hdf5_lite.File(p) as f:
+        layers = W._keras_file_layers(f)
+    assert layers[0][0] == "conv1" and "kernel" in layers[0][1]
