@@ -153,24 +153,27 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_consta
                     tc_fence_after();
                     const uint32_t aA = smem_a0 + st * Cfg::STAGE_BYTES;
                     const uint32_t aB = aA + Cfg::A_BYTES;
-#pragma unroll 1
-                    for (int kk = 0; kk < ksteps; ++kk, ++g) {
-                        const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
-                        const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                        const uint32_t acc_g = g > 0 ? 1u : 0u;
-                        if (NP == 2) {
-                            const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
-                            const uint64_t b_lo = umma_desc_sw128(aB + (BN / 2) * 128 + kk * 32);
-                            if (elect_one()) {
-                                // hi*hi, hi*lo, lo*hi: the order of the single-CTA kernel (bit-identical results)
-                                umma_f16_pair(tacc, a_hi, b_hi, idesc, acc_g);
-                                umma_f16_pair(tacc + cross, a_hi, b_lo, idesc, (g > 0 || one_acc) ? 1u : 0u);
-                                umma_f16_pair(tacc + cross, a_lo, b_hi, idesc, 1u);
+                    const uint64_t dA = umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
+                    const uint64_t dAlo = umma_desc_sw128(aA + 128 * 128), dBlo = umma_desc_sw128(aB + (BN / 2) * 128);
+                    if (elect_one()) {   // one elected region per k-iteration (see conv_tc_persistent.cuh)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < ksteps) {
+                                const uint64_t a_hi = dA + 2 * kk, b_hi = dB + 2 * kk;
+                                const uint32_t acc_g = (g + kk) > 0 ? 1u : 0u;
+                                if (NP == 2) {
+                                    // hi*hi, hi*lo, lo*hi: the order of the single-CTA kernel (bit-identical results)
+                                    const uint64_t a_lo = dAlo + 2 * kk, b_lo = dBlo + 2 * kk;
+                                    umma_f16_pair(tacc, a_hi, b_hi, idesc, acc_g);
+                                    umma_f16_pair(tacc + cross, a_hi, b_lo, idesc, ((g + kk) > 0 || one_acc) ? 1u : 0u);
+                                    umma_f16_pair(tacc + cross, a_lo, b_hi, idesc, 1u);
+                                } else {
+                                    umma_f16_pair(tacc, a_hi, b_hi, idesc, acc_g);
+                                }
                             }
-                        } else {
-                            if (elect_one()) umma_f16_pair(tacc, a_hi, b_hi, idesc, acc_g);
                         }
                     }
+                    g += ksteps;
                     if (elect_one()) umma_commit_pair(&empty_bar[st], 3);  // frees this stage in both CTAs
                     if (++st == STAGES) { st = 0; ph ^= 1; }
                 }

@@ -457,32 +457,37 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                 tc_fence_after();
                 const uint32_t aA = smem_a0 + st * Cfg::STAGE_BYTES;
                 const uint32_t aB = aA + Cfg::A_BYTES;
-#pragma unroll 1
-                for (int kk = 0; kk < ksteps; ++kk, ++g) {
-                    const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
-                    const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                    if (NP == 2) {
-                        const uint64_t a_lo = umma_desc_sw128(aA + 128 * 128 + kk * 32);
-                        const uint32_t acc_g = g > 0 ? 1u : 0u;
-                        if (PC::CONCAT && !one_acc) {
-                            if (elect_one()) {
-                                umma_f16(tacc, a_hi, b_hi, idesc2, acc_g);          // hi*hi -> [0, BN), hi*lo -> [BN, 2 BN)
-                                umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);     // lo*hi -> [BN, 2 BN)
-                            }
-                        } else {
-                            const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                            if (elect_one()) {
-                                // same order of additions into the cross accumulator as the widened scheme above
-                                // (hi*lo, then lo*hi), so every kernel variant produces identical bits
+                // One elected region per k-iteration (<= 4 k16 steps, unrolled): the ELECT / BRA.DIV / BSYNC sequence and the
+                // descriptor set-up are paid once, not per k16 step -- narrow tiles (heads N = 16, stem, ResNet 1x1) were bound
+                // by this issue loop (~100 cycles per MMA), not by the tensor pipe.  Descriptors advance by 32 bytes = 2 units.
+                const uint64_t dA = umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
+                const uint64_t dAlo = umma_desc_sw128(aA + 128 * 128), dBlo = umma_desc_sw128(aB + BN * 128);
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk < ksteps) {
+                            const uint64_t a_hi = dA + 2 * kk, b_hi = dB + 2 * kk;
+                            const uint32_t acc_g = (g + kk) > 0 ? 1u : 0u;
+                            if (NP == 2) {
+                                const uint64_t a_lo = dAlo + 2 * kk;
+                                if (PC::CONCAT && !one_acc) {
+                                    umma_f16(tacc, a_hi, b_hi, idesc2, acc_g);          // hi*hi -> [0, BN), hi*lo -> [BN, 2 BN)
+                                    umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);     // lo*hi -> [BN, 2 BN)
+                                } else {
+                                    // same order of additions into the cross accumulator as the widened scheme above
+                                    // (hi*lo, then lo*hi), so every kernel variant produces identical bits
+                                    const uint64_t b_lo = dBlo + 2 * kk;
+                                    umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
+                                    umma_f16(tacc + cross, a_hi, b_lo, idesc, ((g + kk) > 0 || one_acc) ? 1u : 0u);
+                                    umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);
+                                }
+                            } else {
                                 umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
-                                umma_f16(tacc + cross, a_hi, b_lo, idesc, (g > 0 || one_acc) ? 1u : 0u);
-                                umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);
                             }
                         }
-                    } else {
-                        if (elect_one()) umma_f16(tacc, a_hi, b_hi, idesc, g > 0 ? 1u : 0u);
                     }
                 }
+                g += ksteps;
                 if (elect_one()) umma_commit(&empty_bar[st]);
                 if (++st == nst) { st = 0; ph ^= 1; }
             }

@@ -179,30 +179,32 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
                         tc_fence_after();
                         const uint32_t aA = aSlab + dy * SC::SLAB_W * 128;  // 1024-byte aligned for every dy
                         const uint32_t aB = b0 + bs * SC::B_BYTES;
-#pragma unroll 1
-                        for (int kk = 0; kk < ksteps; ++kk, ++gk) {
-                            const uint64_t a_hi = umma_desc_sw128(aA + kk * 32);
-                            const uint64_t b_hi = umma_desc_sw128(aB + kk * 32);
-                            const uint32_t acc_g = gk > 0 ? 1u : 0u;
-                            if (NP == 2) {
-                                const uint64_t a_lo = umma_desc_sw128(aA + plane_off + kk * 32);
-                                if (!one_acc) {
-                                    if (elect_one()) {
-                                        umma_f16(tacc, a_hi, b_hi, idesc2, acc_g);       // hi*hi -> [0, BN), hi*lo -> [BN, 2 BN)
-                                        umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);  // lo*hi -> [BN, 2 BN)
-                                    }
-                                } else {
-                                    const uint64_t b_lo = umma_desc_sw128(aB + BN * 128 + kk * 32);
-                                    if (elect_one()) {
+                        const uint64_t dA = umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
+                        const uint64_t dAlo = umma_desc_sw128(aA + plane_off), dBlo = umma_desc_sw128(aB + BN * 128);
+                        if (elect_one()) {   // one elected region per tap (see conv_tc_persistent.cuh)
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                if (kk < ksteps) {
+                                    const uint64_t a_hi = dA + 2 * kk, b_hi = dB + 2 * kk;
+                                    const uint32_t acc_g = (gk + kk) > 0 ? 1u : 0u;
+                                    if (NP == 2) {
+                                        const uint64_t a_lo = dAlo + 2 * kk;
+                                        if (!one_acc) {
+                                            umma_f16(tacc, a_hi, b_hi, idesc2, acc_g);       // hi*hi -> [0, BN), hi*lo -> [BN, 2 BN)
+                                            umma_f16(tacc + cross, a_lo, b_hi, idesc, 1u);  // lo*hi -> [BN, 2 BN)
+                                        } else {
+                                            const uint64_t b_lo = dBlo + 2 * kk;
+                                            umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
+                                            umma_f16(tacc, a_hi, b_lo, idesc, 1u);
+                                            umma_f16(tacc, a_lo, b_hi, idesc, 1u);
+                                        }
+                                    } else {
                                         umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
-                                        umma_f16(tacc, a_hi, b_lo, idesc, 1u);
-                                        umma_f16(tacc, a_lo, b_hi, idesc, 1u);
                                     }
                                 }
-                            } else {
-                                if (elect_one()) umma_f16(tacc, a_hi, b_hi, idesc, acc_g);
                             }
                         }
+                        gk += ksteps;
                         if (elect_one()) {
                             if (CL == 1) umma_commit(&b_empty[bs]);
                             else umma_commit_mc(&b_empty[bs], kAll);  // this stage is shared: free it in every CTA

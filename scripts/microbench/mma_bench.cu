@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mode, int feed_kb
                     umma_f16(tm, a_hi, b_hi, idesc, 1u);
                     umma_f16(tm + 256, a_lo, b_hi, idesc, 1u);
                     umma_f16(tm + 256, a_hi, b_lo, idesc, 1u);
+                } else if (mode == 3) {
+                    umma_f16(tm + (kk & 1) * 256, a_hi, b_hi, idesc, 1u);   // two independent accumulation chains
+                } else if (mode == 4) {
+                    umma_f16(tm + kk * 64, a_hi, b_hi, idesc, 1u);          // four independent chains
                 } else {
                     umma_f16_ts(tm, tm + 256 + kk * 8, b_hi, idesc, 1u);
                 }
@@ -122,7 +126,7 @@ void run(const char* name, int mode, int feed, const uint8_t* gsrc, long long* d
     cudaMemcpy(h, dout, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
     long long mx = 0, sum = 0;
     for (int i = 0; i < sms; ++i) { mx = h[i] > mx ? h[i] : mx; sum += h[i]; }
-    const double mmas = static_cast<double>(iters) * ((mode % 10) == 1 ? 12 : 4);
+    const double mmas = static_cast<double>(iters) * ((mode % 10) == 1 ? 12 : 4);   // modes 3 / 4: 4 MMAs per iteration as well
     printf("%-44s N=%3d feed %2d KB/iter : %.1f cycles/MMA (avg over SMs), %.1f (slowest SM); ideal %d\n", name, N, feed, sum / (double)sms / mmas,
            mx / mmas, N / 2);
 }
@@ -134,6 +138,15 @@ int main() {
     cudaMalloc(&gsrc, static_cast<size_t>(sms) * 64 * 1024);
     cudaMemset(gsrc, 0, static_cast<size_t>(sms) * 64 * 1024);
     cudaMalloc(&dout, sizeof(long long) * 256);
+    // narrow tiles: is there a floor per MMA, and is it the dependency through the accumulator?
+    run<16>("SS, 1 chain", 0, 0, gsrc, dout, sms);
+    run<16>("SS, 2 independent chains", 3, 0, gsrc, dout, sms);
+    run<16>("SS, 4 independent chains", 4, 0, gsrc, dout, sms);
+    run<32>("SS, 1 chain", 0, 0, gsrc, dout, sms);
+    run<32>("SS, 2 independent chains", 3, 0, gsrc, dout, sms);
+    run<64>("SS, 1 chain", 0, 0, gsrc, dout, sms);
+    run<64>("SS, 2 independent chains", 3, 0, gsrc, dout, sms);
+    run<128>("SS, 2 independent chains", 3, 0, gsrc, dout, sms);
     for (int feed : {0, 64}) {
         run<128>("SS, 1 MMA per k-step", 0, feed == 0 ? 0 : feed / 2, gsrc, dout, sms);
         run<128>("SS, fp16x3 pattern (3 MMAs per k-step)", 1, feed, gsrc, dout, sms);
