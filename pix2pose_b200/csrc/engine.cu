@@ -154,6 +154,16 @@ struct PlanBuilder {
         const int out = T("act" + tag, Ho, Ho, f3);
         conv(base + "2a", stride == 2 ? K_CONV_S2 : K_CONV, 1, {all(in)}, {{base + "2a", bnb + "2a"}}, ta, ACT_RELU);
         conv(base + "2b", K_CONV, 3, {all(ta)}, {{base + "2b", bnb + "2b"}}, tb, ACT_RELU);
+        static const bool fuse_sc = !getenv("P2P_FUSE_SHORTCUT") || atoi(getenv("P2P_FUSE_SHORTCUT")) != 0;
+        if (shortcut && fuse_sc) {
+            // conv_block (resnet50_mod.py:76-118): relu(BN(conv2c(tb)) + BN(conv1(x))) as ONE contraction over K = [tb | x]
+            // (x sampled at every second pixel in the stride-2 block); saves writing and re-reading the shortcut tensor
+            SrcSpec sx = all(in);
+            sx.view = stride == 2 ? 1 : 0;
+            ConvSpec& c = conv(base + "2c", K_CONV, 1, {all(tb), sx}, {{base + "2c", bnb + "2c"}, {base + "1", bnb + "1"}}, out, ACT_RELU);
+            c.kcat = true;
+            return out;
+        }
         int res = in;
         if (shortcut) {
             res = T("sc" + tag, Ho, Ho, f3);
@@ -194,6 +204,7 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
     for (auto& s : c.srcs) c.Cin += s.c_count;
     c.Cout = 0;
     for (auto& w : c.parts) c.Cout += layer_cout(L[find_layer(L, w.layer)]);
+    if (c.kcat) c.Cout = layer_cout(L[find_layer(L, c.parts[0].layer)]);  // parts add up along K, not along N
     if (c.Cout < 64) { c.BN = 16; c.Cout_pad = 16; }
     else if (c.Cout % 128 == 0) { c.BN = 128; c.Cout_pad = c.Cout; }
     else { c.BN = 64; c.Cout_pad = (c.Cout + 63) / 64 * 64; }
@@ -210,14 +221,14 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         int concat_off = 0;
         for (size_t si = 0; si < c.srcs.size(); ++si) {
             const SrcSpec& s = c.srcs[si];
-            c.maps.push_back({s.tensor, 0, s.c_begin + s.c_count});
+            c.maps.push_back({s.tensor, s.view, s.c_begin + s.c_count});
             const int ks = c.kind == K_PATCH ? 1 : c.ksize;
             for (int kh = 0; kh < ks; ++kh)
                 for (int kw = 0; kw < ks; ++kw)
                     for (int ch = 0; ch < chunks(s.c_count); ++ch) {
                         c.kit.push_back(make_int4(static_cast<int>(si), c.kind == K_PATCH ? 0 : kh - pad,
                                                   c.kind == K_PATCH ? 0 : kw - pad, s.c_begin + ch * 64));
-                        c.kw.push_back({kh, kw, concat_off + ch * 64, std::min(64, s.c_count - ch * 64)});
+                        c.kw.push_back({kh, kw, (c.kcat ? 0 : concat_off) + ch * 64, std::min(64, s.c_count - ch * 64), c.kcat ? static_cast<int>(si) : -1});
                     }
             concat_off += s.c_count;
         }
@@ -628,7 +639,7 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
     for (size_t ci = 0; ci < eng->plan.convs.size(); ++ci) {
         const ConvSpec& c = eng->plan.convs[ci];
         ModelConv& mc = convs[ci];
-        struct PartW { const float* k; const float* b; const float* bn; int cout; const LayerDef* l; };
+        struct PartW { const float* k; const float* b; const float* bn; int cout; const LayerDef* l; std::vector<float> fold; };
         std::vector<PartW> pw;
         float wmax = 0.f;
         for (auto& w : c.parts) {
@@ -640,7 +651,16 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
             q.b = ptr[li] + (L[li].count() - q.cout);
             q.bn = w.bn.empty() ? nullptr : ptr[find_layer(L, w.bn)];
             const size_t nk = L[li].count() - q.cout;
-            for (size_t i = 0; i < nk; ++i) wmax = std::max(wmax, fabsf(q.k[i]));
+            if (c.kcat) {
+                // K-concatenated parts share one epilogue, so each part's BN scale is folded into its weights
+                // (conv kernels are (kh,kw,Cin,Cout): the output channel is the fastest index)
+                P2P_CHECK(q.bn && q.l->kind == L_CONV, "K-concatenated parts must be Conv2D + BatchNormalization");
+                q.fold.resize(q.cout);
+                for (int co = 0; co < q.cout; ++co) q.fold[co] = q.bn[co] / sqrtf(q.bn[3 * q.cout + co] + 1e-3f);
+                for (size_t i = 0; i < nk; ++i) wmax = std::max(wmax, fabsf(q.k[i] * q.fold[i % q.cout]));
+            } else {
+                for (size_t i = 0; i < nk; ++i) wmax = std::max(wmax, fabsf(q.k[i]));
+            }
             pw.push_back(q);
         }
         // power-of-two pre-scale so |w| <= 128: keeps the fp16 lo parts out of the subnormal range
@@ -679,7 +699,9 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
         for (size_t it = 0; c.kind != K_CONVT_FUSED && it < KI; ++it) {
             const KWeight& kw = c.kw[it];
             int n_base = 0;
-            for (auto& q : pw) {
+            for (size_t pi = 0; pi < pw.size(); ++pi) {
+                const PartW& q = pw[pi];
+                if (c.kcat && static_cast<int>(pi) != kw.part) continue;   // this K slice belongs to one part only
                 const LayerDef& l = *q.l;
                 for (int co = 0; co < q.cout; ++co) {
                     const int n = n_base + co;
@@ -700,6 +722,7 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
                         } else {
                             v = q.k[((static_cast<size_t>(kw.kh) * l.shape[1] + kw.kw) * l.shape[2] + cin) * l.shape[3] + co];
                         }
+                        if (c.kcat) v *= q.fold[co];
                         v *= wscale;
                         const __half h = __float2half_rn(v);
                         const size_t o = ((it * np + 0) * c.Cout_pad + n) * 64 + j;
@@ -707,7 +730,7 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
                         if (np == 2) packed[o + static_cast<size_t>(c.Cout_pad) * 64] = __float2half_rn(v - __half2float(h));
                     }
                 }
-                n_base += q.cout;
+                if (!c.kcat) n_base += q.cout;
             }
         }
         std::vector<float> sc(c.Cout_pad, 0.f), sh(c.Cout_pad, 0.f);
@@ -741,10 +764,15 @@ Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
                     s = g / sqrtf(var + 1e-3f);  // keras BatchNormalization epsilon
                     t = be - mu * s + q.b[co] * s;
                 }
-                sc[n_base + co] = s / wscale;
-                sh[n_base + co] = t;
+                if (c.kcat) {               // scales live in the weights; the shifts of the parts add up
+                    sc[co] = 1.f / wscale;
+                    sh[co] += t;
+                } else {
+                    sc[n_base + co] = s / wscale;
+                    sh[n_base + co] = t;
+                }
             }
-            n_base += q.cout;
+            if (!c.kcat) n_base += q.cout;
         }
         mc.packed.upload(packed.data(), packed.size());
         mc.scale.upload(sc.data(), sc.size());

@@ -30,10 +30,10 @@ int parse_backbone(const char* s);
 
 enum ConvKind : int { K_CONV = 0, K_CONV_S2 = 1, K_CONVT = 2, K_DENSE = 3, K_PATCH = 4, K_CONVT_FUSED = 5, K_STEM = 6 };
 
-struct SrcSpec { int tensor, c_begin, c_count; };
+struct SrcSpec { int tensor, c_begin, c_count; int view = 0; };  // view 1: every second pixel of the tensor (stride-2 1x1 source)
 struct WPart { std::string layer, bn; };
 
-struct KWeight { int kh, kw, cin_begin, nvalid; };  // where a k-iteration's 64 K-rows come from
+struct KWeight { int kh, kw, cin_begin, nvalid; int part = -1; };  // where a k-iteration's 64 K-rows come from (part >= 0: K-concatenated conv)
 
 struct ConvSpec {
     std::string name;
@@ -51,6 +51,8 @@ struct ConvSpec {
     std::vector<KWeight> kw;
     struct MapReq { int tensor, view, climit; };  // view: 0 normal, 1..4 parity (py*2+px+1), 5 dense
     std::vector<MapReq> maps;
+    bool kcat = false;                 // parts are concatenated along K (one part per source; BN scales folded into the weights):
+                                       // out = act(sum_p BN_p(conv_p(src_p))) -- the ResNet shortcut conv fused into branch2c
     bool slab = false;                 // runs on conv_tc_slab_kernel (k x k stride-1 conv, Cout 128, W % 8 == 0, H % 16 == 0)
     std::vector<int4> slabs;           // slab kernel: one entry per (source, 64-channel chunk)
 };
