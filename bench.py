@@ -150,7 +150,7 @@ def run_reference(args):
     dt = time.perf_counter() - t
     cores, cvt = cpu_threads()
     val = n / dt
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -274,8 +274,31 @@ def run_ours(args):
                          "sample": "first %d detections of the same workload (%.1f s): torch-CPU fp32 generator (%d threads; stand-in for "
                                    "Keras/TF-CPU) + numpy resize + real cv2.solvePnPRansac (%d threads)" % (args.cpu_sample, cpu_dt, cores, cvthreads)},
     }
-    print(json.dumps(out))
+    emit(out)
     D.shutdown()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (the NCCL version banner, torchrun notices) write to file
+    descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+    saved original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -289,6 +312,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--profile", action="store_true", help="one warm-up + one step only (for ncu launch lists)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
