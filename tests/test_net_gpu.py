@@ -104,3 +104,26 @@ def test_full_size_batch_linearity_property():
     dp, pp = m.predict(x[perm])
     assert np.array_equal(dp, d[perm]) and np.array_equal(pp, p[perm])
     assert np.isfinite(d).all() and np.abs(d).max() <= 1.0 and p.min() >= 0 and p.max() <= 1
+
+
+def test_kernel_variants_agree(inputs, monkeypatch):
+    """The CTA-pair kernel (cta_group::2) must give the SAME BITS as the single-CTA kernel (identical MMA order), the
+    slab-reuse kernel visits the taps in another order and may differ in the last bits only."""
+    from pix2pose_b200 import ae_model
+    w = W.synthetic_weights("resnet50", 1)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = ae_model.GeneratorModel("resnet50", engine=ae_model.Engine("resnet50", 8, "fp16x3"))
+        m.load_weights(w)
+        out = m.predict(inputs)
+        for k in env:
+            monkeypatch.delenv(k)
+        return out
+
+    d0, p0 = run({})
+    d1, p1 = run({"P2P_PAIR": "0"})
+    assert np.array_equal(d0, d1) and np.array_equal(p0, p1)
+    d2, p2 = run({"P2P_SLAB": "0"})
+    assert np.abs(d0 - d2).max() <= 2e-5 and np.abs(p0 - p2).max() <= 2e-5
