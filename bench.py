@@ -267,7 +267,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": conv_traffic(args.capacity), "peak_source": peak_src,
-                     "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one %d-crop forward: %.3f ms; other kernels %.3f ms)" % (
+                     "kernel": "conv_tc_{pair,slab,persistent}_kernel (all %d tcgen05 conv launches of one %d-crop forward: %.3f ms; other kernels %.3f ms)" % (
                          cnt[0], args.capacity, msk[0], msk[1]),
                      "note": "algorithmic FLOPs (10.70 GFLOP/crop); fp16x3 issues 3 MMAs per k-step, so tensor-pipe work is 3x this"},
         "cpu_baseline": {"value": cpu_val, "unit": "crops/s", "cores": cores, "kind": "port",

@@ -489,7 +489,6 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
     P2P_CUDA(cudaGetDevice(&dev));
     P2P_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     P2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    if (const char* e = getenv("P2P_PERSISTENT")) persistent = atoi(e) != 0;
     if (const char* e = getenv("P2P_PAIR")) pair = atoi(e) != 0;
     if (const char* e = getenv("P2P_SLAB")) slab = atoi(e) != 0;
     if (const char* e = getenv("P2P_SLAB_CLUSTER")) slab_cluster = atoi(e);
@@ -864,18 +863,6 @@ void launch_conv_pair(const CUtensorMap* mA, const CUtensorMap& mBh, const CUten
     P2P_CUDA(cudaGetLastError());
 }
 
-template <int BN, int NP>
-void launch_conv(const CUtensorMap* mA, const CUtensorMap& mB, const ConvParams& p, dim3 grid, cudaStream_t s) {
-    using Cfg = ConvCfg<BN, NP>;
-    static bool configured = false;
-    if (!configured) {
-        P2P_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
-    conv_tc_kernel<BN, NP><<<grid, 192, Cfg::SMEM_BYTES, s>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
-    P2P_CUDA(cudaGetLastError());
-}
-
 }  // namespace
 
 void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, float* prob_dev, const int* n_active,
@@ -958,7 +945,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     max_steps = std::max(max_steps, steps);
                     max_nk = std::max(max_nk, ke - kb);
                 }
-                p.single_acc = (persistent && np == 2 && max_steps <= single_acc_steps) ? 1 : 0;
+                p.single_acc = (np == 2 && max_steps <= single_acc_steps) ? 1 : 0;
             }
             if (const char* e = getenv("P2P_DBG")) p.dbg = atoi(e);
             p.Cout_pad = c.Cout_pad;
@@ -971,14 +958,13 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             const int tiles_n = (n + c.nb - 1) / c.nb;
             dim3 grid(p.tiles_x * p.tiles_y * tiles_n, c.Cout_pad / c.BN, c.splitk > 1 ? c.splitk : c.phases);
             p.grid_m = grid.x; p.grid_n = grid.y; p.grid_z = grid.z;
-            P2P_CHECK(c.BN != 256 || persistent, "BN = 256 tiles need the persistent kernel");
             // N = 128 tiles stay on the single-CTA kernel: a cta_group::2 MMA seems to cost >= ~100 cycles whatever its width,
             // so three N = 128 pair MMAs per k-step ran 40-50 % slower than the widened two of the single-CTA kernel
             // (deconv3 1627 -> 2452 us); at N = 256 the pair wins (conv4 499 -> 438 us).  P2P_PAIR_BN128=1 = experiment.
             static const int pair_min_bn = getenv("P2P_PAIR_BN128") && atoi(getenv("P2P_PAIR_BN128")) ? 128 : 256;
-            const bool use_pair = persistent && pair && c.BN >= pair_min_bn && c.splitk <= 1 && c.kind != K_DENSE && c.act != ACT_HEADS &&
+            const bool use_pair = pair && c.BN >= pair_min_bn && c.splitk <= 1 && c.kind != K_DENSE && c.act != ACT_HEADS &&
                                   c.res_tensor < 0 && rt.has_out && tma_store && grid.x >= 2;
-            if (persistent && slab && c.slab && rt.has_out && tma_store) {
+            if (slab && c.slab && rt.has_out && tma_store) {
                 p.tma_store = 1;
                 p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
                 p.slab_ksize = c.ksize;
@@ -1008,7 +994,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     if (np == 2) launch_conv_pair<128, 2>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
                     else launch_conv_pair<128, 1>(rt.mapA, mc.mapBh, rt.mapOut, p, pairs, s);
                 }
-            } else if (persistent) {
+            } else {
                 p.tma_store = (tma_store && rt.has_out) ? 1 : 0;
                 {
                     // epilogue-bound layers (few k-iterations per tile) run on fewer operand stages and use the freed
@@ -1040,14 +1026,6 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                     else if (c.BN == 64) launch_conv_persistent<64, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
                     else launch_conv_persistent<16, 1>(rt.mapA, mc.mapB, rt.mapOut, rt.mapRes, p, ctas, s);
                 }
-            } else if (np == 2) {
-                if (c.BN == 128) launch_conv<128, 2>(rt.mapA, mc.mapB, p, grid, s);
-                else if (c.BN == 64) launch_conv<64, 2>(rt.mapA, mc.mapB, p, grid, s);
-                else launch_conv<16, 2>(rt.mapA, mc.mapB, p, grid, s);
-            } else {
-                if (c.BN == 128) launch_conv<128, 1>(rt.mapA, mc.mapB, p, grid, s);
-                else if (c.BN == 64) launch_conv<64, 1>(rt.mapA, mc.mapB, p, grid, s);
-                else launch_conv<16, 1>(rt.mapA, mc.mapB, p, grid, s);
             }
             ++launches;
             mark(0);

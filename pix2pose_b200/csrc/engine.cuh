@@ -112,7 +112,6 @@ class Engine {
                               // 2 gains 1 %, 4 loses 75 % to cluster placement -- the layer is bound by shared-memory bandwidth, not by L2)
     bool slab = true;         // slab-reuse kernel for the Cout-128 k x k convs (P2P_SLAB=0 disables)
     bool pair = true;         // CTA-pair kernel (cta_group::2, M = 256) for the wide decoder convs (P2P_PAIR=0 disables)
-    bool persistent = true;   // conv_tc_persistent_kernel (default; P2P_PERSISTENT=0 selects the one-tile-per-CTA kernel)
 
     // x_dev -> dec_dev / prob_dev for n <= cap crops; n_active (device int) optionally limits work further.
     void forward(const Model& m, const float* x_dev, int n, float* dec_dev, float* prob_dev, const int* n_active,
