@@ -217,20 +217,45 @@ __global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restric
 }
 
 // compact candidate numbering over the batch + per-chunk live counts for the stage-2 forwards
-__global__ void cand_scan_kernel(DetState* __restrict__ state, CandStats* __restrict__ cands, int n_det, int* __restrict__ n_active,
-                                 int n_chunks, int chunk) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int base = 0;
-    for (int d = 0; d < n_det; ++d) {
-        state[d].cand_base = base;
-        for (int k = 0; k < state[d].n_cand; ++k) {
-            cands[base + k].det = d;
-            cands[base + k].k = k;
+// One block of 256 threads: thread t owns detections t, t + 256, ...; block-wide exclusive scan of n_cand per round (a single
+// thread walking the 900-byte DetState records paid one global-load latency per detection: 144 us for 256 detections).
+__global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ state, CandStats* __restrict__ cands, int n_det,
+                                                        int* __restrict__ n_active, int n_chunks, int chunk) {
+    __shared__ int s_w[8];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int d0 = 0; d0 < n_det; d0 += 256) {
+        const int d = d0 + threadIdx.x;
+        const int nc = d < n_det ? state[d].n_cand : 0;
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        base += state[d].n_cand;
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int base = s_carry;
+        for (int w = 0; w < warp; ++w) base += s_w[w];
+        base += incl - nc;
+        if (d < n_det) {
+            state[d].cand_base = base;
+            for (int k = 0; k < nc; ++k) {
+                cands[base + k].det = d;
+                cands[base + k].k = k;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = base + nc;
+        __syncthreads();
     }
-    for (int j = 0; j < n_chunks; ++j) n_active[j] = max(0, min(chunk, base - j * chunk));
-    n_active[n_chunks] = base;  // total
+    if (threadIdx.x == 0) {
+        const int total = s_carry;
+        for (int j = 0; j < n_chunks; ++j) n_active[j] = max(0, min(chunk, total - j * chunk));
+        n_active[n_chunks] = total;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,7 +581,7 @@ void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, 
     P2P_CUDA(cudaGetLastError());
     const int C = n * n_th;
     const int n_chunks = (C + cap - 1) / cap;
-    cand_scan_kernel<<<1, 32, 0, s>>>(state_.p, cands_.p, n, n_active_.p, n_chunks, cap);
+    cand_scan_kernel<<<1, 256, 0, s>>>(state_.p, cands_.p, n, n_active_.p, n_chunks, cap);
     P2P_CUDA(cudaGetLastError());
     // stage 2
     crop_resize_kernel<true><<<dim3(C, 64), 256, 0, s>>>(frames_dev, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
