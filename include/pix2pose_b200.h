@@ -122,6 +122,10 @@ P2P_API int p2p_pipeline_run_device(p2p_pipeline_t* p, const p2p_model_t* m, con
                             int iters, double confidence, p2p_pose_t* out);
 /* After a run: winner's uint8 XYZ crop (h,w,3) and valid mask (h,w), h = best_box[5]-best_box[4], w = [7]-[6]. */
 P2P_API int p2p_pipeline_fetch_crop(p2p_pipeline_t* p, int det, const p2p_pose_t* rec, uint8_t* xyz, uint8_t* mask);
+/* After a run: mask-IoU ingredients of tools/5_evaluation_bop_basic.py:307-316 on the device.  masks: (n,H,W) uint8 detector
+ * instance masks of the first n detections of the last run (host); out: n x {|mask_pred & m|, |mask_pred | m|} where mask_pred
+ * is the full-frame mask est_pose returns (recognition.py:170-178). */
+P2P_API int p2p_pipeline_mask_iou(p2p_pipeline_t* p, const uint8_t* masks, int n, int H, int W, long long* out);
 /* Raw (128,128,3) network output: stage 1 (index = detection) or stage 2 (index = cand_base + k). */
 P2P_API int p2p_pipeline_fetch_decode(p2p_pipeline_t* p, int stage, int index, float* out);
 /* Debug / parity: raw float buffers of the last run. what: 1 dec1, 2 dec2, 3 x1, 4 x2 ((128,128,3)), 5 prob1, 6 prob2 ((128,128)). */

@@ -67,6 +67,8 @@ def lib():
         "p2p_pipeline_fetch_crop": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8)]),
         "p2p_pipeline_fetch_decode": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
         "p2p_pipeline_fetch_buffer": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_pipeline_mask_iou": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_longlong)]),
         "p2p_pipeline_set_box_size": (ctypes.c_int, [vp, ctypes.c_double]),
         "p2p_pipeline_debug_override": (ctypes.c_int, [vp, ctypes.c_int, c_f, c_f, ctypes.c_int]),
         "p2p_pipeline_launch_count": (ctypes.c_longlong, [vp]),

@@ -156,6 +156,12 @@ int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decod
         p->p->set_override(stage, decode, prob, n);
     });
 }
+int p2p_pipeline_mask_iou(p2p_pipeline_t* p, const uint8_t* masks, int n, int H, int W, long long* out) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->mask_iou(masks, n, H, W, out);
+    });
+}
 int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size) {
     return guarded([&] {
         P2P_CHECK(p, "NULL argument");

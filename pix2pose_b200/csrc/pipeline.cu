@@ -514,6 +514,45 @@ __global__ void select_kernel(const DetIn* __restrict__ dets, const DetState* __
     recs[d] = r;
 }
 
+// P6: mask IoU of the estimated pose's mask against the detector's instance mask (tools/5_evaluation_bop_basic.py:307-316):
+// mask_pred is the full-frame bool array est_pose returns (zeros, the winner's valid mask pasted at best_box; all-true inside
+// the box when PnP returned inliers = None, recognition.py:177, :219).  One CTA per detection counts |A and B| and |A or B|.
+__global__ void __launch_bounds__(256) mask_iou_kernel(const DetIn* __restrict__ dets, const PoseRecord* __restrict__ recs,
+                                                       const uint8_t* __restrict__ valid, const uint8_t* __restrict__ det_masks,
+                                                       int H, int W, long long* __restrict__ out) {
+    const int d = blockIdx.x;
+    const PoseRecord& r = recs[d];
+    const DetIn& di = dets[d];
+    const bool has = r.status == 1 && r.best_cand >= 0;
+    const int v1 = r.best_box[4], v2 = r.best_box[5], u1 = r.best_box[6], u2 = r.best_box[7];
+    const int w = u2 - u1;
+    const long long pool = di.pool_off + static_cast<long long>(has ? r.best_cand : 0) * di.cap_px;
+    const uint8_t* m = det_masks + static_cast<long long>(d) * H * W;
+    int inter = 0, uni = 0;
+    for (int p = threadIdx.x; p < H * W; p += blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        const bool a = m[p] != 0;
+        bool b = false;
+        if (has && y >= v1 && y < v2 && x >= u1 && x < u2) b = r.mask_all_true || valid[pool + static_cast<long long>(y - v1) * w + (x - u1)] != 0;
+        inter += (a && b) ? 1 : 0;
+        uni += (a || b) ? 1 : 0;
+    }
+    __shared__ int s_i[8], s_u[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inter += __shfl_xor_sync(0xffffffffu, inter, o);
+        uni += __shfl_xor_sync(0xffffffffu, uni, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_i[threadIdx.x >> 5] = inter; s_u[threadIdx.x >> 5] = uni; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long ti = 0, tu = 0;
+        for (int k = 0; k < 8; ++k) { ti += s_i[k]; tu += s_u[k]; }
+        out[2 * d] = ti;
+        out[2 * d + 1] = tu;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -619,6 +658,22 @@ void Pipeline::fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_
     const size_t npx = static_cast<size_t>(std::max(h, 0)) * std::max(w, 0);
     if (xyz_out) P2P_CUDA(cudaMemcpy(xyz_out, xyz_u8_.p + pool * 3, npx * 3, cudaMemcpyDeviceToHost));
     if (mask_out) P2P_CUDA(cudaMemcpy(mask_out, valid_.p + pool, npx, cudaMemcpyDeviceToHost));
+}
+
+void Pipeline::mask_iou(const uint8_t* masks_host, int n, int H, int W, long long* inter_union_out) {
+    P2P_CHECK(masks_host && inter_union_out, "NULL argument");
+    P2P_CHECK(n >= 0 && n <= static_cast<int>(host_dets_.size()), "mask_iou: %d masks for %zu detections of the last run", n, host_dets_.size());
+    if (n == 0) return;
+    cudaStream_t s = engine->stream;
+    const size_t bytes = static_cast<size_t>(n) * H * W;
+    if (det_masks_.n < bytes) det_masks_.alloc(bytes);
+    if (iou_.n < static_cast<size_t>(2 * n)) iou_.alloc(2 * n);
+    P2P_CUDA(cudaMemcpyAsync(det_masks_.p, masks_host, bytes, cudaMemcpyHostToDevice, s));
+    mask_iou_kernel<<<n, 256, 0, s>>>(dets_.p, recs_.p, valid_.p, det_masks_.p, H, W, iou_.p);
+    P2P_CUDA(cudaGetLastError());
+    ++launches;
+    P2P_CUDA(cudaMemcpyAsync(inter_union_out, iou_.p, sizeof(long long) * 2 * n, cudaMemcpyDeviceToHost, s));
+    P2P_CUDA(cudaStreamSynchronize(s));
 }
 
 void Pipeline::fetch_decode(int stage, int index, float* out) {

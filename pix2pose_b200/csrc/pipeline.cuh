@@ -75,6 +75,9 @@ class Pipeline {
     // After run(): copy the winner's uint8 XYZ crop (h,w,3) and valid mask (h,w) of detection d
     // (h = v2-v1, w = u2-u1 of best_box) into host buffers sized for cap_px pixels.
     void fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out);
+    // After run(): |mask_pred and m_d| and |mask_pred or m_d| for the first n detections against detector masks (n,H,W) uint8
+    // (host), mask_pred being the full-frame mask est_pose returns; out = n x {intersection, union}.
+    void mask_iou(const uint8_t* masks_host, int n, int H, int W, long long* inter_union_out);
     // Raw network output (128,128,3) of stage 1 (index = detection) or stage 2 (index = compact candidate).
     void fetch_decode(int stage, int index, float* out);
     // Debug / parity: raw float buffers. what: 1 dec1, 2 dec2, 3 x1, 4 x2 ((128,128,3) each), 5 prob1, 6 prob2 ((128,128)).
@@ -104,7 +107,8 @@ class Pipeline {
     DevBuf<float> obj_, img_;
     DevBuf<PnpProblem> problems_;
     DevBuf<PnpResult> pnp_res_;
-    DevBuf<uint8_t> frames_;
+    DevBuf<uint8_t> frames_, det_masks_;
+    DevBuf<long long> iou_;
     std::vector<float> ov_dec_[2], ov_prob_[2];
     long long pool_px_ = 0;
     std::vector<DetIn> host_dets_;

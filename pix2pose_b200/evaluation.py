@@ -31,8 +31,17 @@ def est_pose_loop(recognizers, image, rois, obj_orders, r_ids):
     return {r: recognizers[obj_orders[r]].est_pose(image, np.asarray(rois[r]).astype(int)) for r in r_ids}
 
 
-def est_pose_batched(recognizers, image, rois, obj_orders, r_ids):
-    """B200 backend: one ``est_pose_batch`` per object; returns the same 6-tuples as ``est_pose``."""
+class DeviceMaskIoU:
+    """Stands in for ``mask_pred`` in the batched backend when the detector masks are known: |mask_pred & m| and
+    |mask_pred | m| were counted on the device, so no mask crosses the bus."""
+
+    def __init__(self, inter, union):
+        self.inter, self.union = int(inter), int(union)
+
+
+def est_pose_batched(recognizers, image, rois, obj_orders, r_ids, masks=None):
+    """B200 backend: one ``est_pose_batch`` per object; returns the same 6-tuples as ``est_pose``.  With ``masks``
+    ((H,W,n_rois) detector masks, the reference's layout) the mask entry is a ``DeviceMaskIoU``."""
     out = {}
     by_obj = {}
     for r in r_ids:
@@ -41,9 +50,15 @@ def est_pose_batched(recognizers, image, rois, obj_orders, r_ids):
     for order, rs in by_obj.items():
         rec = recognizers[order]
         res = rec.est_pose_batch(image, [np.asarray(rois[r]).astype(int) for r in rs])
+        iou = None
+        if masks is not None and masks.shape[:2] == (H, W):
+            iou = res.mask_iou(np.ascontiguousarray(np.moveaxis(np.asarray(masks)[:, :, rs], 2, 0)))
         for i, r in enumerate(rs):
             if res.status[i] != 1:
                 out[r] = (None, -1, -1, -1, -1, res.bbox_t[i])
+                continue
+            if iou is not None:
+                out[r] = (None, DeviceMaskIoU(iou[0][i], iou[1][i]), res.R[i], res.t[i], res.frac_inlier[i], res.bbox_t[i])
                 continue
             xyz, mask, bx = res.crop(i)
             full = np.zeros((H, W), bool)
@@ -60,7 +75,8 @@ def recognize_image(recognizers, image, rois, obj_orders, obj_ids, scores, masks
     for rec in recognizers:
         rec.camK = np.asarray(cam_K).reshape(3, 3)                               # :302
     keep = select_rois(rois, obj_ids, obj_id_targets, inst_counts, cand_factor)
-    poses = backend(recognizers, image, rois, obj_orders, keep)
+    use_dev_iou = backend is est_pose_batched and score_type == 2 and detect_type == "rcnn" and masks is not None
+    poses = backend(recognizers, image, rois, obj_orders, keep, masks=masks) if use_dev_iou else backend(recognizers, image, rois, obj_orders, keep)
     result_score, result_objid, result_R, result_t = [], [], [], []
     for r_id in keep:
         img_pred, mask_pred, rot_pred, tra_pred, frac_inlier, bbox_t = poses[r_id]
@@ -70,8 +86,11 @@ def recognize_image(recognizers, image, rois, obj_orders, obj_ids, scores, masks
             m = masks[:, :, r_id]
             if m.shape[:2] != image.shape[:2]:
                 raise ValueError("detector mask must have the image size (the reference resizes with skimage; not reproduced)")
-            union = np.sum(np.logical_or(m, mask_pred))
-            mask_iou = 0 if union <= 0 else np.sum(np.logical_and(m, mask_pred)) / union
+            if isinstance(mask_pred, DeviceMaskIoU):
+                union, inter = mask_pred.union, mask_pred.inter
+            else:
+                union, inter = np.sum(np.logical_or(m, mask_pred)), np.sum(np.logical_and(m, mask_pred))
+            mask_iou = 0 if union <= 0 else inter / union
             score = scores[r_id] * frac_inlier * mask_iou * union
         else:
             score = scores[r_id]

@@ -116,6 +116,19 @@ class PoseBatchResult:
         """(img_pred uint8 (h,w,3), valid_mask bool (h,w), box) of detection d's winning candidate."""
         return self._owner._fetch_crop(d, self._poses[d])
 
+    def mask_iou(self, masks):
+        """Device-side mask IoU ingredients (tools/5_evaluation_bop_basic.py:307-316): ``masks`` (n,H,W) bool/uint8 detector
+        masks of this batch's detections -> (intersection (n,), union (n,)) with the full-frame ``mask_pred`` est_pose
+        returns.  Must be called before the next run of the (shared) pipeline."""
+        m = np.ascontiguousarray(np.asarray(masks).astype(np.uint8))
+        if m.ndim != 3 or m.shape[0] != self.n:
+            raise ValueError("masks must be (n,H,W) with n = %d detections, got %s" % (self.n, m.shape))
+        out = np.zeros((self.n, 2), np.int64)
+        if self.n:
+            _lib.check(_lib.lib().p2p_pipeline_mask_iou(self._owner._pipe, m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.n,
+                                                        m.shape[1], m.shape[2], out.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
+        return out[:, 0].copy(), out[:, 1].copy()
+
 
 class pix2pose():
     def __init__(self, weight_fn, camK, res_x, res_y, obj_param, th_ransac=3.0, th_outlier=[0.1, 0.2, 0.3], th_inlier=0.1,

@@ -193,3 +193,23 @@ def test_evaluation_loop_batched_equals_per_roi(frame):
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert x["obj_id"] == y["obj_id"] and x["score"] == y["score"] and np.array_equal(x["R"], y["R"]) and np.array_equal(x["t"], y["t"])
+
+
+def test_device_mask_iou_matches_numpy(rec, frame):
+    """|mask_pred & m| and |mask_pred | m| counted on the device equal numpy on the full-frame masks
+    (tools/5_evaluation_bop_basic.py:307-316)."""
+    rng = np.random.RandomState(11)
+    rois = [[197, 277, 283, 363], [100, 200, 260, 330], [-20, -10, 90, 120], [50, 60, 300, 420]]
+    res = rec.est_pose_batch(frame, [np.array(r) for r in rois])
+    masks = rng.rand(len(rois), 480, 640) > 0.5
+    for i, r in enumerate(rois):
+        masks[i, :max(r[0], 0)] = False
+        masks[i, :, r[3]:] = False
+    inter, union = res.mask_iou(masks)
+    for i in range(len(rois)):
+        full = np.zeros((480, 640), bool)
+        if res.status[i] == 1:
+            _, m, bx = res.crop(i)
+            full[bx[4]:bx[5], bx[6]:bx[7]] = m
+        assert inter[i] == np.sum(full & masks[i]) and union[i] == np.sum(full | masks[i]), i
+    assert (res.status == 1).any()
