@@ -159,6 +159,15 @@ P2P_API void p2p_host_free(void* p);
  * forward as (n,H,W,C) fp32; *h,*w,*c receive the shape. `out` may be NULL to query the shape. */
 P2P_API int p2p_engine_read_tensor(p2p_engine_t* e, const char* name, int n, float* out, int* h, int* w, int* c);
 
+/* ---- depth -> ICP inputs (pix2pose_util/common_util.py:13-90; callers tools/5_evaluation_bop_icp3d.py:78-79,
+ * ros_kinetic/ros_pix2pose.py:180-181, 296-297).  Host buffers, float64, bbox = [v0,u0,v1,u1] or NULL for the whole image.
+ * p2p_depth_xyz      = getXYZ(depth, fx, fy, cx, cy, bbox)                           -> out (h,w,3)
+ * p2p_depth_normals  = get_normal(...) after its cv2.inpaint step: Gaussian smoothing with `sigma` (2 in the reference;
+ *                      0 = refine=False), np.gradient(.., 2, edge_order=2) on the bbox crop, unit normals -> out (h,w,3) */
+P2P_API int p2p_depth_xyz(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox, double* out);
+P2P_API int p2p_depth_normals(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox,
+                              double sigma, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,11 @@ def lib():
         "p2p_pipeline_fetch_crop": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8)]),
         "p2p_pipeline_fetch_decode": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
         "p2p_pipeline_fetch_buffer": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_depth_xyz": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
+        "p2p_depth_normals": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_int), ctypes.c_double,
+                                             ctypes.POINTER(ctypes.c_double)]),
         "p2p_pipeline_mask_iou": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_longlong)]),
         "p2p_pipeline_set_box_size": (ctypes.c_int, [vp, ctypes.c_double]),

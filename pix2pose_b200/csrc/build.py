@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libpix2pose_b200.so")
-SOURCES = ["engine.cu", "pnp_ransac.cu", "pipeline.cu", "capi.cu"]
+SOURCES = ["engine.cu", "pnp_ransac.cu", "pipeline.cu", "depth.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-Xcompiler", "-Wall", "-cudart", "static"]

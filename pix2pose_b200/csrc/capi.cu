@@ -7,6 +7,11 @@
 
 using namespace p2p;
 
+namespace p2p {  // csrc/depth.cu
+void depth_xyz(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox, double* out);
+void depth_normals(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox, double sigma, double* out);
+}
+
 struct p2p_engine { std::unique_ptr<Engine> e; };
 struct p2p_model { std::unique_ptr<Model> m; };
 struct p2p_pipeline { std::unique_ptr<Pipeline> p; };
@@ -155,6 +160,13 @@ int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const float* decod
         P2P_CHECK(p, "NULL argument");
         p->p->set_override(stage, decode, prob, n);
     });
+}
+int p2p_depth_xyz(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox, double* out) {
+    return guarded([&] { depth_xyz(depth, H, W, fx, fy, cx, cy, bbox, out); });
+}
+int p2p_depth_normals(const double* depth, int H, int W, double fx, double fy, double cx, double cy, const int* bbox, double sigma,
+                      double* out) {
+    return guarded([&] { depth_normals(depth, H, W, fx, fy, cx, cy, bbox, sigma, out); });
 }
 int p2p_pipeline_mask_iou(p2p_pipeline_t* p, const uint8_t* masks, int n, int H, int W, long long* out) {
     return guarded([&] {
