@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the depth helpers of the reference's ICP path,
 ``pix2pose_util/common_util.py:13-90`` (``getXYZ``, ``get_normal``), with numpy / scipy / cv2 exactly as the reference
 calls them (only ``np.float`` -> ``float``, removed in numpy >= 1.24).  Checker for ``pix2pose_b200/depth.py``;
-never imported by the product."""
+never imported by the product.  PINNED: unlike the network half, this part of the reference imports here (numpy, cv2,
+scipy only), so tests/golden/depth_golden.npz holds outputs of the reference's own functions
+(tests/golden/make_depth_golden.py) and tests/test_oracle_depth.py checks this restatement against them exactly."""
 import cv2
 import numpy as np
 from scipy import ndimage

@@ -59,3 +59,19 @@ def test_flat_plane_normal_and_degenerate_inputs():
     z = D.get_normal(np.zeros((32, 32)), bbox=np.array([0]), refine=False, **K)
     assert np.array_equal(z, np.zeros((32, 32, 3)))             # zero cross product -> norm set to 1 -> zeros
     assert D.getXYZ(np.zeros((8, 8)), 1.0, 1.0, 0.0, 0.0, np.array([2, 2, 2, 5])).shape == (0, 3, 3)
+
+
+def test_against_golden_vectors_of_the_reference_functions():
+    """tests/golden/depth_golden.npz = outputs of pix2pose_util/common_util.py itself (tests/golden/make_depth_golden.py)."""
+    import os
+    from pix2pose_b200 import depth as D
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "depth_golden.npz"))
+    fx, fy, cx, cy = g["K"]
+    box = g["bbox"]
+    kw = dict(fx=fx, fy=fy, cx=cx, cy=cy)
+    assert np.array_equal(D.getXYZ(g["depth_plain"], fx, fy, cx, cy), g["xyz_full"])
+    assert np.array_equal(D.getXYZ(g["depth_plain"], fx, fy, cx, cy, box), g["xyz_box"])
+    assert np.array_equal(D.get_normal(g["depth_plain"], bbox=np.array([0]), refine=False, **kw), g["normal_full"])
+    assert np.array_equal(D.get_normal(g["depth_plain"], bbox=box, refine=False, **kw), g["normal_box"])
+    assert np.abs(D.get_normal(g["depth_holes"].copy(), bbox=np.array([0]), refine=True, **kw) - g["normal_refined_full"]).max() <= 1e-9
+    assert np.abs(D.get_normal(g["depth_holes"].copy(), bbox=box, refine=True, **kw) - g["normal_refined_box"]).max() <= 1e-9

@@ -1,7 +1,27 @@
 """CPU checks of oracle/depth_oracle.py (restatement of pix2pose_util/common_util.py:13-90): analytic cases."""
+import os
+
 import numpy as np
 
 from oracle import depth_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "depth_golden.npz")
+
+
+def test_oracle_equals_the_reference_functions_on_the_golden_vectors():
+    """tests/golden/depth_golden.npz holds outputs of the REFERENCE's own getXYZ / get_normal
+    (pix2pose_util/common_util.py, run by tests/golden/make_depth_golden.py in the build container): this pins the
+    restatement -- same numpy / scipy / cv2 calls, so the match is exact."""
+    g = np.load(GOLD)
+    fx, fy, cx, cy = g["K"]
+    box = g["bbox"]
+    assert np.array_equal(O.getXYZ(g["depth_plain"], fx, fy, cx, cy), g["xyz_full"])
+    assert np.array_equal(O.getXYZ(g["depth_plain"], fx, fy, cx, cy, box), g["xyz_box"])
+    kw = dict(fx=fx, fy=fy, cx=cx, cy=cy)
+    assert np.array_equal(O.get_normal(g["depth_plain"], bbox=np.array([0]), refine=False, **kw), g["normal_full"])
+    assert np.array_equal(O.get_normal(g["depth_plain"], bbox=box, refine=False, **kw), g["normal_box"])
+    assert np.allclose(O.get_normal(g["depth_holes"].copy(), bbox=np.array([0]), refine=True, **kw), g["normal_refined_full"], atol=1e-12)
+    assert np.allclose(O.get_normal(g["depth_holes"].copy(), bbox=box, refine=True, **kw), g["normal_refined_box"], atol=1e-12)
 
 
 def test_getxyz_backprojects_pixels():
