@@ -4,9 +4,21 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``pix2pose_b200/`` (the product) may im
 this package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
 baseline / ``--impl reference`` legs do, and only as the checker / the timed CPU arm.
 
-Parity status: the reference has no tests, golden vectors or fixtures
-and cannot be imported here (needs keras 2.2.1 / tensorflow-gpu 1.9 / scikit-image);
-*parity unpinned* for the network and resize halves -- the restatement below is pinned
-only by algebraic self-checks (tests/test_oracle_*.py).  The PnP half calls the real
-``cv2.solvePnPRansac`` (container OpenCV 4.13.0; reference pins 3.4.2.17).
+Parity status: the reference has no tests, golden vectors or fixtures and
+its modules cannot be imported here (keras 2.2.1 / tensorflow-gpu 1.9 / scikit-image at
+module level).  What IS pinned by the reference's own code, executed in the build container
+and committed as golden vectors (scripts under tests/golden/):
+
+* ``pix2pose.get_boxes``, ``pix2pose.pnp_ransac`` and the whole ``pix2pose.est_pose`` control flow
+  (recognition.py:28-224): the method definitions are compiled out of the reference file in
+  memory and run with numpy / cv2; ``resize`` and ``generator_train.predict`` are injected
+  (oracle resize, planted analytic maps).  tests/test_reference_golden.py: the oracle returns
+  exactly the same boxes, crops, masks, R|t, inlier fractions and sentinels.
+* ``pix2pose_util/common_util.py`` ``getXYZ`` / ``get_normal`` (imports here unmodified):
+  tests/test_oracle_depth.py.
+
+*Parity unpinned* remains for the two third-party semantics that cannot run here: the
+Keras/TensorFlow network arithmetic (net_oracle.py, pinned only by algebraic self-checks) and
+scikit-image ``resize`` (resize_oracle.py, documented behaviour of skimage 0.14-0.18).  The PnP
+itself is the real ``cv2.solvePnPRansac`` (container OpenCV 4.13.0; reference pins 3.4.2.17).
 """
