@@ -16,9 +16,15 @@ and committed as golden vectors (scripts under tests/golden/):
   exactly the same boxes, crops, masks, R|t, inlier fractions and sentinels.
 * ``pix2pose_util/common_util.py`` ``getXYZ`` / ``get_normal`` (imports here unmodified):
   tests/test_oracle_depth.py.
+* the network TOPOLOGY: ``ae_model.aemodel_unet_resnet50`` / ``aemodel_unet_prob`` and
+  ``resnet50_mod.ResNet50`` are executed on tests/fake_keras.py (a stand-in for the Keras functional
+  API whose layers evaluate with net_oracle's primitives); net_oracle's hand-written forward gives
+  the same bits as the graph the reference code builds, and the construction order of the
+  weight-carrying layers is the one the Keras-HDF5 importer assumes (tests/test_oracle_net.py).
 
 *Parity unpinned* remains for the two third-party semantics that cannot run here: the
-Keras/TensorFlow network arithmetic (net_oracle.py, pinned only by algebraic self-checks) and
+Keras/TensorFlow per-layer arithmetic (TF 'same' padding, Conv2DTranspose cropping, BatchNorm epsilon, LeakyReLU
+alpha as restated in net_oracle.py; algebraic self-checks only) and
 scikit-image ``resize`` (resize_oracle.py, documented behaviour of skimage 0.14-0.18).  The PnP
 itself is the real ``cv2.solvePnPRansac`` (container OpenCV 4.13.0; reference pins 3.4.2.17).
 """

@@ -3,6 +3,7 @@ SURVEY.md §8a and the committed golden vectors."""
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -63,3 +64,42 @@ def test_fp64_mode_agrees():
     d32, _ = NetOracle(w, "paper").forward(x)
     d64, _ = NetOracle(w, "paper", torch.float64).forward(x)
     assert np.abs(d32 - d64).max() < 1e-4
+
+
+# ---- pinned by the reference's own model-building code (tests/golden/make_topology_golden.py) ---------------------------
+def _topology_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "topology_golden.npz"))
+
+
+@pytest.mark.parametrize("backbone", ["resnet50", "paper"])
+def test_forward_equals_the_graph_built_by_the_reference_code(backbone):
+    """tests/golden/topology_golden.npz: ae_model.py / resnet50_mod.py of the reference EXECUTED on a fake Keras whose layers
+    use this oracle's primitives.  Equal bits => the hand-written forward wires every layer exactly like the reference
+    (inputs, strides, paddings, channel slices f1[:32] / f2[:128] / f3[:128], concatenation order, head order)."""
+    from oracle.net_oracle import NetOracle
+    from pix2pose_b200 import weights as W
+    g = _topology_golden()
+    x = np.random.RandomState(0).uniform(-1, 1, (2, 128, 128, 3)).astype(np.float32)
+    d, p = NetOracle(W.synthetic_weights(backbone, 1), backbone).forward(x)
+    assert np.array_equal(d[:, ::4, ::4], g[backbone + "_decode_s4"])
+    assert np.array_equal(p[:, ::4, ::4], g[backbone + "_prob_s4"])
+
+
+@pytest.mark.parametrize("backbone", ["resnet50", "paper"])
+def test_keras_import_follows_the_reference_construction_order(backbone):
+    """The weight-carrying layers in the order the reference code constructs them (Keras names: explicit ones and the
+    auto-numbered batch_normalization_k / dense_k / conv2d_transpose_k) mapped by weights.keras_layers_to_weights give back
+    every tensor in its place -- the importer's name / per-kind-order rule matches the reference's construction order."""
+    from pix2pose_b200 import weights as W
+    g = _topology_golden()
+    w = W.synthetic_weights(backbone, 4)
+    kinds = {n: k for n, k, _ in W.layer_table(backbone)}
+    file_layers = []
+    for kname, tname in zip(g[backbone + "_keras_order"], g[backbone + "_table_order"]):
+        kname, tname = str(kname), str(tname)
+        keys = ("gamma", "beta", "moving_mean", "moving_variance") if kinds[tname] == W.BN else ("kernel", "bias")
+        file_layers.append((kname, {k: w[tname + "/" + k] for k in keys}))
+    assert len(file_layers) == len(kinds)
+    got = W.keras_layers_to_weights(file_layers, backbone)
+    assert all(np.array_equal(got[k], w[k]) for k in W.param_names(backbone))
