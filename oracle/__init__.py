@@ -16,6 +16,8 @@ and committed as golden vectors (scripts under tests/golden/):
   exactly the same boxes, crops, masks, R|t, inlier fractions and sentinels.
 * ``pix2pose_util/common_util.py`` ``getXYZ`` / ``get_normal`` (imports here unmodified):
   tests/test_oracle_depth.py.
+* the per-image loop of tools/5_evaluation_bop_basic.py:281-349 (those source lines exec'd on seeded
+  detections): tests/test_evaluation_host.py checks pix2pose_b200/evaluation.py against it.
 * the network TOPOLOGY: ``ae_model.aemodel_unet_resnet50`` / ``aemodel_unet_prob`` and
   ``resnet50_mod.ResNet50`` are executed on tests/fake_keras.py (a stand-in for the Keras functional
   API whose layers evaluate with net_oracle's primitives); net_oracle's hand-written forward gives

@@ -61,11 +61,11 @@ def reference_loop(recs, image, rois, obj_orders, obj_ids, scores, masks, target
     return out
 
 
-def test_recognize_image_matches_reference_loop(tmp_path):
+def detections():
+    """Seeded detector output of one image (shared with tests/golden/make_evaluation_golden.py)."""
     rng = np.random.RandomState(0)
     image = rng.randint(0, 256, (120, 160, 3)).astype(np.uint8)
     targets, inst_counts = [3, 7, 9], [1, 2, 1]
-    recs = [FakeRec(3), FakeRec(7), FakeRec(9)]
     n = 14
     rois = [[rng.randint(0, 60), rng.randint(0, 80), rng.randint(61, 120), rng.randint(81, 160)] for _ in range(n)]
     rois[4] = [-1, -1, 5, 5]
@@ -74,6 +74,30 @@ def test_recognize_image_matches_reference_loop(tmp_path):
     scores = rng.uniform(0.5, 1.0, n)
     masks = rng.rand(120, 160, n) > 0.5
     K = np.array([572.4, 0, 80, 0, 573.5, 60, 0, 0, 1.0])
+    return image, targets, inst_counts, rois, obj_ids, obj_orders, scores, masks, K
+
+
+def test_recognize_image_equals_the_reference_drivers_own_loop():
+    """tests/golden/evaluation_golden.npz: lines 281-349 of tools/5_evaluation_bop_basic.py exec'd on these detections
+    (tests/golden/make_evaluation_golden.py).  Same rows, same order, same scores, for both score types and both tasks."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "evaluation_golden.npz"))
+    image, targets, inst_counts, rois, obj_ids, obj_orders, scores, masks, K = detections()
+    for score_type in (1, 2):
+        for task_type in ("1", "2"):
+            recs = [FakeRec(t) for t in targets]
+            got = E.recognize_image(recs, image, rois, obj_orders, obj_ids, scores, masks, targets, inst_counts, K, scene_id=5, im_id=9,
+                                    cand_factor=2, score_type=score_type, task_type=task_type, backend=E.est_pose_loop)
+            key = "s%d_t%s" % (score_type, task_type)
+            assert [r["obj_id"] for r in got] == list(g[key + "_obj"]) and len(got) > 0
+            assert np.array_equal(np.array([r["score"] for r in got]), g[key + "_score"])
+            assert np.array_equal(np.array([r["R"] for r in got]), g[key + "_R"])
+            assert np.array_equal(np.array([r["t"] for r in got]), g[key + "_t"])
+
+
+def test_recognize_image_matches_reference_loop(tmp_path):
+    image, targets, inst_counts, rois, obj_ids, obj_orders, scores, masks, K = detections()
+    recs = [FakeRec(3), FakeRec(7), FakeRec(9)]
     for score_type in (1, 2):
         for task_type in ("1", "2"):
             want = reference_loop(recs, image, rois, obj_orders, obj_ids, scores, masks, targets, inst_counts, K, 2, score_type, task_type)
