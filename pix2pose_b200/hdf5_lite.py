@@ -468,14 +468,28 @@ class Writer:
         return 0x000C, body
 
     @staticmethod
-    def _header(msgs):
+    def _msg_bytes(msgs):
         body = b""
         for mtype, data in msgs:
             data = data.ljust(_pad8(len(data)), b"\x00")
             body += struct.pack("<HHBBBB", mtype, len(data), 0, 0, 0, 0) + data
+        return body
+
+    @classmethod
+    def _header(cls, msgs, alloc=None, split=False):
+        """Version-1 object header.  ``split``: everything after the first message goes into a continuation block (what
+        libhdf5 does when attributes are added to an object whose header chunk is full)."""
+        if split and alloc is not None and len(msgs) > 1:
+            tail = cls._msg_bytes(msgs[1:])
+            caddr = alloc(tail)
+            first = cls._msg_bytes([msgs[0], (0x0010, struct.pack("<QQ", caddr, len(tail)))])
+            return struct.pack("<BBHII", 1, 0, len(msgs) + 1, 1, len(first)) + b"\x00" * 4 + first
+        body = cls._msg_bytes(msgs)
         return struct.pack("<BBHII", 1, 0, len(msgs), 1, len(body)) + b"\x00" * 4 + body
 
-    def save(self, path):
+    def save(self, path, leaf_k=4, internal_k=16, split_headers=True):
+        """Writes the file.  Defaults mimic libhdf5: at most 2 * leaf_k symbols per SNOD, 2 * internal_k children per B-tree
+        node (so groups with many members get multi-level B-trees) and attributes in object-header continuation blocks."""
         out = bytearray(96)           # superblock placeholder
 
         def alloc(blob):
@@ -503,17 +517,35 @@ class Writer:
                 heap_data.extend(e.ljust(_pad8(len(e)), b"\x00"))
             data_addr = alloc(bytes(heap_data))
             heap_addr = alloc(b"HEAP" + struct.pack("<BBBBQQQ", 0, 0, 0, 0, len(heap_data), UNDEF, data_addr))
-            snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
-            for o, a in zip(offs, addrs):
-                snod += struct.pack("<QQII", o, a, 0, 0) + b"\x00" * 16
-            snod_addr = alloc(snod)
-            tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, snod_addr, offs[-1] if offs else 0)
-            tree_addr = alloc(tree)
+            # leaves: symbol-table nodes of up to 2 * leaf_k entries, in name order
+            cap = 2 * leaf_k
+            level = []                                # (address, heap offset of the largest name below)
+            for i in range(0, max(len(names), 1), cap):
+                part = list(zip(offs[i:i + cap], addrs[i:i + cap]))
+                snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(part))
+                for o, a in part:
+                    snod += struct.pack("<QQII", o, a, 0, 0) + b"\x00" * 16
+                snod += b"\x00" * (40 * (cap - len(part)))
+                level.append((alloc(snod), part[-1][0] if part else 0))
+            depth = 0
+            while True:                               # B-tree levels until one node is left
+                nodes, fan = [], 2 * internal_k
+                for i in range(0, len(level), fan):
+                    part = level[i:i + fan]
+                    tree = b"TREE" + struct.pack("<BBHQQ", 0, depth, len(part), UNDEF, UNDEF) + struct.pack("<Q", 0)
+                    for addr, key in part:
+                        tree += struct.pack("<QQ", addr, key)
+                    nodes.append((alloc(tree), part[-1][1]))
+                level, depth = nodes, depth + 1
+                if len(level) == 1:
+                    break
+            tree_addr = level[0][0]
             node._symtab = (tree_addr, heap_addr)
-            return alloc(self._header([(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + msgs))
+            hdr = [(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + msgs
+            return alloc(self._header(hdr, alloc, split_headers and len(msgs) > 0))
 
         root_addr = emit(self.root)
-        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4096, 16, 0)
+        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, leaf_k, internal_k, 0)
         sb += struct.pack("<QQQQ", 0, UNDEF, len(out), UNDEF)
         sb += struct.pack("<QQII", 0, root_addr, 1, 0) + struct.pack("<QQ", *self.root._symtab)
         out[:96] = sb

@@ -33,6 +33,31 @@ def test_reader_roundtrip_of_groups_datasets_attributes(tmp_path):
             f["g1/zzz"]
 
 
+def test_many_members_multi_level_btree_and_header_continuation(tmp_path):
+    """Groups as libhdf5 lays them out for a ~100-layer Keras file: 8 symbols per SNOD, 32 children per B-tree node (here
+    300 members -> 38 leaves -> a two-level tree), attributes in an object-header continuation block."""
+    w = hdf5_lite.Writer()
+    names = ["layer_%03d" % i for i in range(300)]
+    for i, n in enumerate(names):
+        w.create_dataset("%s/%s/kernel:0" % (n, n), np.full((2, 3), float(i), np.float32))
+        w.set_attr(n, "weight_names", np.array([("%s/kernel:0" % n).encode()]))
+    w.set_attr("", "layer_names", np.array([n.encode() for n in names]))
+    w.set_attr("", "backend", np.array(b"tensorflow"))
+    p = str(tmp_path / "many.h5")
+    w.save(p)                                          # leaf_k = 4, internal_k = 16, split headers
+    with hdf5_lite.File(p) as f:
+        assert f.keys() == names
+        assert [v.decode() for v in f.attrs["layer_names"]] == names and f.attrs["backend"] == b"tensorflow"
+        for i in (0, 7, 8, 255, 256, 299):
+            g = f[names[i]]
+            assert g.attrs["weight_names"][0].decode() == names[i] + "/kernel:0"
+            assert np.array_equal(np.asarray(g[names[i] + "/kernel:0"]), np.full((2, 3), float(i), np.float32))
+    q = str(tmp_path / "flat.h5")
+    w.save(q, leaf_k=4096, internal_k=16, split_headers=False)    # one SNOD per group, attributes in the first header chunk
+    with hdf5_lite.File(q) as f:
+        assert f.keys() == names and np.asarray(f["layer_123/layer_123/kernel:0"])[0, 0] == 123.0
+
+
 def test_rejects_non_hdf5_and_names_unsupported_features(tmp_path):
     p = tmp_path / "x.hdf5"
     p.write_bytes(b"not an hdf5 file" * 10)
