@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--capacity", type=int, default=256)
-    ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--cpu-sample", type=int, default=96)    # ~15 s of CPU work on 16 cores
     ap.add_argument("--profile", action="store_true", help="one warm-up + one step only (for ncu launch lists)")
     args = ap.parse_args()
     quiet_stdout()
