@@ -10,6 +10,9 @@ SOURCES = ["engine.cu", "pnp_ransac.cu", "pipeline.cu", "depth.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-Xcompiler", "-Wall", "-cudart", "static"]
+# The EPnP/RANSAC kernels restate OpenCV's double-precision arithmetic operation by operation (csrc/epnp_core.cuh):
+# no mul+add contraction there, explicit fma() only where the original has one.
+EXTRA_FLAGS = {"pnp_ransac.cu": ["-fmad=false"]}
 
 
 def _newest(paths):
@@ -26,7 +29,7 @@ def build(force=False, verbose=False):
     objs = []
     for s in srcs:
         o = os.path.join(HERE, os.path.basename(s)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(os.path.basename(s), []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         subprocess.check_call(cmd)
         objs.append(o)
     cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs

@@ -157,131 +157,193 @@ P2P_HD inline void tridiag_eig_sym(double* A, double* Vt, double* w) {
     }
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major `A`, destroyed).
-// On return w[0] >= w[1] >= ... and row i of `Vt` is the unit eigenvector of w[i]
-// (the layout of cvSVD(..., CV_SVD_U_T) that epnp.cpp indexes as ut + 12*i).
-template <int N>
-P2P_HD inline void jacobi_eig_sym(double* A, double* Vt, double* w) {
-    for (int i = 0; i < N; ++i)
-        for (int j = 0; j < N; ++j) Vt[i * N + j] = (i == j) ? 1.0 : 0.0;
-    // Rotations whose off-diagonal element is below eps * ||A||_F are skipped; a sweep without any
-    // rotation ends the iteration (rank-deficient 5-point systems would otherwise spin on noise).
-    double fro = 0.0;
-    for (int i = 0; i < N * N; ++i) fro += A[i] * A[i];
-    const double tiny = 1e-17 * sqrt(fro);
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        bool rotated = false;
-        for (int p = 0; p < N - 1; ++p)
-            for (int q = p + 1; q < N; ++q) {
-                const double apq = A[p * N + q];
-                if (fabs(apq) <= tiny) continue;
-                rotated = true;
-                const double app = A[p * N + p], aqq = A[q * N + q];
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < N; ++k) {  // columns p,q
-                    const double akp = A[k * N + p], akq = A[k * N + q];
-                    A[k * N + p] = c * akp - s * akq;
-                    A[k * N + q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < N; ++k) {  // rows p,q
-                    const double apk = A[p * N + k], aqk = A[q * N + k];
-                    A[p * N + k] = c * apk - s * aqk;
-                    A[q * N + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < N; ++k) {  // eigenvectors (stored as rows)
-                    const double vpk = Vt[p * N + k], vqk = Vt[q * N + k];
-                    Vt[p * N + k] = c * vpk - s * vqk;
-                    Vt[q * N + k] = s * vpk + c * vqk;
-                }
-            }
-        if (!rotated) break;
+// ---------------------------------------------------------------------------------------------------------------
+// Bit-exact restatement of the OpenCV linear algebra EPnP goes through (modules/core/src/lapack.cpp of the image's
+// cv2 4.13.0; its arithmetic was read off the shipped binary and every routine below is checked BITWISE against
+// cv2.SVDecomp / cv2.invert(DECOMP_SVD) / cv2.solve(DECOMP_SVD) / cv2.mulTransposed in tests/test_epnp_host.py).
+// Why bit-exact: with exactly 5 correspondences (the RANSAC minimal set) M^T M has a 2-D null space and EPnP reads the
+// LEFT singular vectors, which for (numerically) zero singular values are the normalised rounding residue of the
+// one-sided Jacobi iteration -- a chaotic function of every rounding upstream.  Matching cv2's hypotheses therefore
+// needs the same operations in the same order: sequential (non-pairwise) sums, no FMA contraction (this header is
+// compiled with -fmad=false / -ffp-contract=off), OpenCV's own hypot, its rotation formulas and its descending
+// selection sort.
+// Element (i,k) of a matrix lives at A[(i*cols + k) * S]: S = 1 on the host, S = blockDim on the device when the
+// matrix is interleaved across the threads of a block in shared memory.
+
+P2P_HD inline double cv_hypot(double a, double b) {   // lapack.cpp's local hypot, NOT libm's
+    a = fabs(a);
+    b = fabs(b);
+    if (a > b) {
+        b /= a;
+        return a * sqrt(1 + b * b);
     }
-    for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
-    for (int i = 0; i < N - 1; ++i) {  // selection sort, descending
-        int m = i;
-        for (int j = i + 1; j < N; ++j)
-            if (w[j] > w[m]) m = j;
-        if (m != i) {
-            const double tw = w[i]; w[i] = w[m]; w[m] = tw;
-            for (int k = 0; k < N; ++k) { const double tv = Vt[i * N + k]; Vt[i * N + k] = Vt[m * N + k]; Vt[m * N + k] = tv; }
-        }
+    if (b > 0) {
+        a /= b;
+        return b * sqrt(1 + a * a);
     }
+    return 0;
 }
 
-// One-sided (Hestenes) Jacobi SVD of an M x N matrix (row-major, N <= M <= 6): A = U diag(s) V^T.
-// `A` is overwritten by U*diag(s) column-wise; returns s (descending) and V (N x N, row-major,
-// columns = right singular vectors) with U's columns normalised in place where s > 0.
-template <int M, int N>
-P2P_HD inline void jacobi_svd(double* A, double* s, double* V) {
-    for (int i = 0; i < N; ++i)
-        for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        bool rotated = false;
-        for (int p = 0; p < N - 1; ++p)
-            for (int q = p + 1; q < N; ++q) {
-                double a = 0, b = 0, g = 0;
-                for (int k = 0; k < M; ++k) {
-                    a += A[k * N + p] * A[k * N + p];
-                    b += A[k * N + q] * A[k * N + q];
-                    g += A[k * N + p] * A[k * N + q];
-                }
-                if (g == 0.0 || fabs(g) <= 1e-16 * sqrt(a * b)) continue;
-                rotated = true;
-                const double zeta = (b - a) / (2.0 * g);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-                for (int k = 0; k < M; ++k) {
-                    const double x = A[k * N + p], y = A[k * N + q];
-                    A[k * N + p] = c * x - sn * y;
-                    A[k * N + q] = sn * x + c * y;
-                }
-                for (int k = 0; k < N; ++k) {
-                    const double x = V[k * N + p], y = V[k * N + q];
-                    V[k * N + p] = c * x - sn * y;
-                    V[k * N + q] = sn * x + c * y;
-                }
-            }
-        if (!rotated) break;
-    }
-    for (int j = 0; j < N; ++j) {
-        double n2 = 0;
-        for (int k = 0; k < M; ++k) n2 += A[k * N + j] * A[k * N + j];
-        s[j] = sqrt(n2);
-    }
-    for (int i = 0; i < N - 1; ++i) {  // sort descending, permuting columns of A and V
-        int m = i;
-        for (int j = i + 1; j < N; ++j)
-            if (s[j] > s[m]) m = j;
-        if (m != i) {
-            const double ts = s[i]; s[i] = s[m]; s[m] = ts;
-            for (int k = 0; k < M; ++k) { const double t = A[k * N + i]; A[k * N + i] = A[k * N + m]; A[k * N + m] = t; }
-            for (int k = 0; k < N; ++k) { const double t = V[k * N + i]; V[k * N + i] = V[k * N + m]; V[k * N + m] = t; }
+// JacobiSVDImpl_<double>: one-sided Jacobi on the N rows (length M) of At.  On return W = singular values
+// (descending), rows i < N1 of At scaled to unit length (= rows of U^T), Vt (if WANT_V) = V^T.
+template <int M, int N, bool WANT_V, int N1, int S = 1>
+P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
+    const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
+#define P2P_AT(i, k) At[((i) * M + (k)) * S]
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+        W[i] = sd;
+        if (WANT_V) {
+            for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
+            Vt[i * N + i] = 1;
         }
     }
-    for (int j = 0; j < N; ++j)
-        if (s[j] > 0.0)
-            for (int k = 0; k < M; ++k) A[k * N + j] /= s[j];
+    const int max_iter = M > 30 ? M : 30;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < M; ++k) p += P2P_AT(i, k) * P2P_AT(j, k);
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = cv_hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < M; ++k) {
+                    const double x = P2P_AT(i, k), y = P2P_AT(j, k);
+                    const double t0 = c * x + s * y;
+                    const double t1 = -s * x + c * y;
+                    P2P_AT(i, k) = t0;
+                    P2P_AT(j, k) = t1;
+                    a += t0 * t0;
+                    b += t1 * t1;
+                }
+                W[i] = a;
+                W[j] = b;
+                changed = true;
+                if (WANT_V)
+                    for (int k = 0; k < N; ++k) {
+                        const double x = Vt[i * N + k], y = Vt[j * N + k];
+                        Vt[i * N + k] = c * x + s * y;
+                        Vt[j * N + k] = -s * x + c * y;
+                    }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < N - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < N; ++k)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(j, k); P2P_AT(j, k) = t; }
+            if (WANT_V)
+                for (int k = 0; k < N; ++k) { const double t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+        }
+    }
+    // unit rows; a singular value <= DBL_MIN gets a vector regenerated from the fixed-seed RNG and orthogonalised
+    // against the previous rows (exactly rank-deficient input, e.g. coplanar points with one coordinate constant)
+    unsigned long long rng = 0x12345678ull;
+    for (int i = 0; i < N1; ++i) {
+        double sd = W[i];
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / M;
+            for (int k = 0; k < M; ++k) {
+                rng = (unsigned long long)(unsigned)rng * 4164903690ull + (unsigned)(rng >> 32);
+                P2P_AT(i, k) = ((unsigned)rng & 256) != 0 ? val0 : -val0;
+            }
+            for (int it = 0; it < 2; ++it)
+                for (int j = 0; j < i; ++j) {
+                    sd = 0;
+                    for (int k = 0; k < M; ++k) sd += P2P_AT(i, k) * P2P_AT(j, k);
+                    double asum = 0;
+                    for (int k = 0; k < M; ++k) {
+                        const double t = P2P_AT(i, k) - sd * P2P_AT(j, k);
+                        P2P_AT(i, k) = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < M; ++k) P2P_AT(i, k) *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+            sd = sqrt(sd);
+        }
+        const double sc = sd > minval ? 1 / sd : 0.;
+        for (int k = 0; k < M; ++k) P2P_AT(i, k) *= sc;
+    }
+#undef P2P_AT
 }
 
-// Minimum-norm least squares x = pinv(A) b through the SVD, singular values below
-// 2*DBL_EPSILON*sum(s) dropped (cv::solve(..., DECOMP_SVD) / SVD::backSubst).
-template <int M, int N>
-P2P_HD inline void svd_solve(const double* A_in, const double* b, double* x) {
-    double A[M * N], s[N], V[N * N];
-    for (int i = 0; i < M * N; ++i) A[i] = A_in[i];
-    jacobi_svd<M, N>(A, s, V);
+// cv::SVD::compute(A, w, u, vt) for a 3x3 A (row-major): ut = U^T (rows = left singular vectors), vt = V^T.
+P2P_HD inline void cv_svd3(const double* A, double* w, double* ut, double* vt) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) ut[i * 3 + j] = A[j * 3 + i];
+    cv_jacobi_svd<3, 3, true, 3>(ut, w, vt);
+}
+// same without V (cvSVD(A, W, Ut, 0, CV_SVD_U_T))
+P2P_HD inline void cv_svd3_ut(const double* A, double* ut, double* w) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) ut[i * 3 + j] = A[j * 3 + i];
+    cv_jacobi_svd<3, 3, false, 3>(ut, w, nullptr);
+}
+
+// cvInvert(A, Ainv, CV_SVD) for 3x3: SVD::compute + SVD::backSubst (SVBkSbImpl_ with an identity right-hand side).
+P2P_HD inline void cv_invert3_svd(const double* A, double* x) {
+    double w[3], ut[9], vt[9];
+    cv_svd3(A, w, ut, vt);
+    for (int i = 0; i < 9; ++i) x[i] = 0;
     double thr = 0;
-    for (int j = 0; j < N; ++j) thr += s[j];
-    thr *= 2.0 * 2.220446049250313e-16;
-    for (int i = 0; i < N; ++i) x[i] = 0.0;
-    for (int j = 0; j < N; ++j) {
-        if (!(s[j] > thr)) continue;
-        double ub = 0;
-        for (int k = 0; k < M; ++k) ub += A[k * N + j] * b[k];
-        ub /= s[j];
-        for (int i = 0; i < N; ++i) x[i] += V[i * N + j] * ub;
+    for (int i = 0; i < 3; ++i) thr += w[i];
+    thr *= 2.220446049250313e-16 * 2;
+    for (int i = 0; i < 3; ++i) {
+        double wi = w[i];
+        if (fabs(wi) <= thr) continue;
+        wi = 1 / wi;
+        double buf[3];
+        for (int j = 0; j < 3; ++j) buf[j] = ut[i * 3 + j] * wi;
+        for (int r = 0; r < 3; ++r) {
+            const double s = vt[i * 3 + r];
+            for (int j = 0; j < 3; ++j) x[r * 3 + j] = x[r * 3 + j] + s * buf[j];
+        }
+    }
+}
+
+// cvSolve(A, b, x, CV_SVD) for a 6 x N system (N <= 5): minimum-norm least squares, singular values
+// <= 2*DBL_EPSILON*sum(w) dropped.
+template <int N>
+P2P_HD inline void cv_solve6_svd(const double* A, const double* b, double* x) {
+    double at[N * 6], w[N], vt[N * N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < 6; ++j) at[i * 6 + j] = A[j * N + i];
+    cv_jacobi_svd<6, N, true, N>(at, w, vt);
+    for (int i = 0; i < N; ++i) x[i] = 0;
+    double thr = 0;
+    for (int i = 0; i < N; ++i) thr += w[i];
+    thr *= 2.220446049250313e-16 * 2;
+    for (int i = 0; i < N; ++i) {
+        double wi = w[i];
+        if (fabs(wi) <= thr) continue;
+        wi = 1 / wi;
+        double s = 0;
+        for (int j = 0; j < 6; ++j) s += at[i * 6 + j] * b[j];
+        s *= wi;
+        for (int j = 0; j < N; ++j) x[j] = x[j] + s * vt[i * N + j];
     }
 }
 
@@ -290,12 +352,14 @@ P2P_HD inline bool qr_solve_6x4(double* A, double* b, double* x) {
     const int nr = 6, nc = 4;
     double A1[4], A2[4];
     for (int k = 0; k < nc; ++k) {
-        double eta = 0;
-        for (int i = k; i < nr; ++i) eta = fmax(eta, fabs(A[i * nc + k]));
+        // epnp.cpp's pivot scan reads each element BEFORE advancing its pointer, so it covers rows k .. nr-2 only
+        double eta = fabs(A[k * nc + k]);
+        for (int i = k; i < nr - 1; ++i) eta = fmax(eta, fabs(A[i * nc + k]));
         if (eta == 0.0) return false;  // singular: OpenCV leaves X untouched
+        const double inv_eta = 1. / eta;
         double sigma = 0;
         for (int i = k; i < nr; ++i) {
-            A[i * nc + k] /= eta;
+            A[i * nc + k] *= inv_eta;
             sigma += A[i * nc + k] * A[i * nc + k];
         }
         sigma = sqrt(sigma);
@@ -325,76 +389,6 @@ P2P_HD inline bool qr_solve_6x4(double* A, double* b, double* x) {
     return true;
 }
 
-// Left singular vectors of a 3x3 matrix exactly as OpenCV's JacobiSVDImpl_ (modules/core/src/lapack.cpp)
-// produces them for cvSVD(A, W, Ut, 0, CV_SVD_U_T): one-sided Jacobi on the ROWS of A^T with its
-// rotation formulas, descending sort, rows normalised.  EPnP's control points are c0 + k*u_i, so the
-// SIGN convention of u_i changes the (noisy-data) solution at the 1e-3 level: it must be OpenCV's.
-// ut: rows = singular vectors, w: singular values.
-P2P_HD inline void cv_svd3_ut(const double* A, double* ut, double* w) {
-    const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
-    double At[9], W[3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) At[i * 3 + j] = A[j * 3 + i];
-    for (int i = 0; i < 3; ++i) {
-        double sd = 0;
-        for (int k = 0; k < 3; ++k) sd += At[i * 3 + k] * At[i * 3 + k];
-        W[i] = sd;
-    }
-    for (int iter = 0; iter < 30; ++iter) {
-        bool changed = false;
-        for (int i = 0; i < 2; ++i)
-            for (int j = i + 1; j < 3; ++j) {
-                double* Ai = At + i * 3;
-                double* Aj = At + j * 3;
-                double a = W[i], p = 0, b = W[j];
-                for (int k = 0; k < 3; ++k) p += Ai[k] * Aj[k];
-                if (fabs(p) <= eps * sqrt(a * b)) continue;
-                p *= 2;
-                const double beta = a - b, gamma = hypot(p, beta);
-                double c, sn;
-                if (beta < 0) {
-                    const double delta = (gamma - beta) * 0.5;
-                    sn = sqrt(delta / gamma);
-                    c = p / (gamma * sn * 2);
-                } else {
-                    c = sqrt((gamma + beta) / (gamma * 2));
-                    sn = p / (gamma * c * 2);
-                }
-                a = b = 0;
-                for (int k = 0; k < 3; ++k) {
-                    const double t0 = c * Ai[k] + sn * Aj[k];
-                    const double t1 = -sn * Ai[k] + c * Aj[k];
-                    Ai[k] = t0; Aj[k] = t1;
-                    a += t0 * t0; b += t1 * t1;
-                }
-                W[i] = a; W[j] = b;
-                changed = true;
-            }
-        if (!changed) break;
-    }
-    for (int i = 0; i < 3; ++i) {
-        double sd = 0;
-        for (int k = 0; k < 3; ++k) sd += At[i * 3 + k] * At[i * 3 + k];
-        W[i] = sqrt(sd);
-    }
-    for (int i = 0; i < 2; ++i) {
-        int j = i;
-        for (int k = i + 1; k < 3; ++k)
-            if (W[j] < W[k]) j = k;
-        if (i != j) {
-            const double tw = W[i]; W[i] = W[j]; W[j] = tw;
-            for (int k = 0; k < 3; ++k) { const double t = At[i * 3 + k]; At[i * 3 + k] = At[j * 3 + k]; At[j * 3 + k] = t; }
-        }
-    }
-    for (int i = 0; i < 3; ++i) {
-        w[i] = W[i];
-        // (OpenCV regenerates the vector from a fixed-seed RNG when W[i] <= DBL_MIN; such exactly
-        //  degenerate point sets -- collinear / identical points -- are left as a zero vector here.)
-        const double sc = W[i] > minval ? 1.0 / W[i] : 0.0;
-        for (int k = 0; k < 3; ++k) ut[i * 3 + k] = At[i * 3 + k] * sc;
-    }
-}
-
 // ---- control points (epnp.cpp choose_control_points) from the centroid and the 3x3 scatter
 // PW0^T PW0 of the n reference points.
 P2P_HD inline void choose_control_points(const double* centroid, const double* scatter, int n, double cws[4][3]) {
@@ -407,20 +401,12 @@ P2P_HD inline void choose_control_points(const double* centroid, const double* s
     }
 }
 
-// cc_inv of compute_barycentric_coordinates: pseudo-inverse (cvInvert CV_SVD) of [c1-c0 c2-c0 c3-c0].
+// cc_inv of compute_barycentric_coordinates: cvInvert(CC, CC_inv, CV_SVD) of [c1-c0 c2-c0 c3-c0].
 P2P_HD inline void control_inverse(const double cws[4][3], double* ci) {
-    double cc[9], s[3], V[9];
+    double cc[9];
     for (int i = 0; i < 3; ++i)
         for (int j = 1; j < 4; ++j) cc[3 * i + j - 1] = cws[j][i] - cws[0][i];
-    jacobi_svd<3, 3>(cc, s, V);  // cc now holds U
-    double thr = (s[0] + s[1] + s[2]) * 2.0 * 2.220446049250313e-16;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double acc = 0;
-            for (int k = 0; k < 3; ++k)
-                if (s[k] > thr) acc += V[i * 3 + k] * cc[j * 3 + k] / s[k];
-            ci[i * 3 + j] = acc;
-        }
+    cv_invert3_svd(cc, ci);
 }
 
 P2P_HD inline void barycentric(const double* ci, const double cws[4][3], const double* p, double* a) {
@@ -475,14 +461,14 @@ P2P_HD inline void compute_rho(const double cws[4][3], double* rho) {
 P2P_HD inline void find_betas_approx_1(const double* l, const double* rho, double* betas) {  // [B11 B12 B13 B14]
     double L[24], b4[4];
     for (int i = 0; i < 6; ++i) { L[i * 4] = l[i * 10]; L[i * 4 + 1] = l[i * 10 + 1]; L[i * 4 + 2] = l[i * 10 + 3]; L[i * 4 + 3] = l[i * 10 + 6]; }
-    svd_solve<6, 4>(L, rho, b4);
+    cv_solve6_svd<4>(L, rho, b4);
     if (b4[0] < 0) { betas[0] = sqrt(-b4[0]); betas[1] = -b4[1] / betas[0]; betas[2] = -b4[2] / betas[0]; betas[3] = -b4[3] / betas[0]; }
     else { betas[0] = sqrt(b4[0]); betas[1] = b4[1] / betas[0]; betas[2] = b4[2] / betas[0]; betas[3] = b4[3] / betas[0]; }
 }
 P2P_HD inline void find_betas_approx_2(const double* l, const double* rho, double* betas) {  // [B11 B12 B22]
     double L[18], b3[3];
     for (int i = 0; i < 6; ++i) { L[i * 3] = l[i * 10]; L[i * 3 + 1] = l[i * 10 + 1]; L[i * 3 + 2] = l[i * 10 + 2]; }
-    svd_solve<6, 3>(L, rho, b3);
+    cv_solve6_svd<3>(L, rho, b3);
     if (b3[0] < 0) { betas[0] = sqrt(-b3[0]); betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
     else { betas[0] = sqrt(b3[0]); betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
     if (b3[1] < 0) betas[0] = -betas[0];
@@ -492,7 +478,7 @@ P2P_HD inline void find_betas_approx_3(const double* l, const double* rho, doubl
     double L[30], b5[5];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 5; ++j) L[i * 5 + j] = l[i * 10 + j];
-    svd_solve<6, 5>(L, rho, b5);
+    cv_solve6_svd<5>(L, rho, b5);
     if (b5[0] < 0) { betas[0] = sqrt(-b5[0]); betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
     else { betas[0] = sqrt(b5[0]); betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
     if (b5[1] < 0) betas[0] = -betas[0];
@@ -520,16 +506,65 @@ P2P_HD inline void gauss_newton(const double* l, const double* rho, double* beta
     }
 }
 
-// From the 12x12 M^T M: the four eigenvectors of the smallest eigenvalues (rows of ut8) and the three refined
-// beta sets (epnp.cpp compute_pose, middle part).
-P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
-    double w[12], l[60], rho[6];
-    tridiag_eig_sym<12, 8>(mtm, ut8, w);
+// The three refined beta sets from the four null-space candidates ut8 (rows 8..11 of U^T) -- epnp.cpp compute_pose,
+// middle part.
+P2P_HD inline void betas_from_ut(const double* ut8, const double cws[4][3], double betas[3][4]) {
+    double l[60], rho[6];
     compute_L_6x10(ut8, l);
     compute_rho(cws, rho);
     find_betas_approx_1(l, rho, betas[0]); gauss_newton(l, rho, betas[0]);
     find_betas_approx_2(l, rho, betas[1]); gauss_newton(l, rho, betas[1]);
     find_betas_approx_3(l, rho, betas[2]); gauss_newton(l, rho, betas[2]);
+}
+
+// Large-n refit path: the eigenvectors of the four smallest eigenvalues of M^T M by tridiagonal QL (for n >= 6 noisy
+// points they are well separated, so any accurate eigen-solver agrees with cv2 to ~1e-13; signs cancel in the betas).
+P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
+    double w[12];
+    tridiag_eig_sym<12, 8>(mtm, ut8, w);
+    betas_from_ut(ut8, cws, betas);
+}
+
+// Small-n path, bit-exact: cvSVD(MtM, D, Ut, 0, CV_SVD_MODIFY_A | CV_SVD_U_T) in place on `mtm` (element stride S),
+// rows 8..11 copied out.
+template <int S = 1>
+P2P_HD inline void solve_betas_exact(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
+    double w[12];
+    cv_jacobi_svd<12, 12, false, 12, S>(mtm, w, nullptr);   // MtM is bitwise symmetric, so A^T = A
+    for (int i = 0; i < 48; ++i) ut8[i] = mtm[(96 + i) * S];
+    betas_from_ut(ut8, cws, betas);
+}
+
+// cvMulTransposed(M, MtM, 1) for the 2n x 12 matrix fill_M builds, restated on its sparsity: per entry the same
+// products in the same (row-sequential) order; the structural zeros contribute exact +-0 and are skipped.
+// `mtm` (stride S) receives the full symmetric matrix.
+template <int S = 1>
+P2P_HD inline void mtm_exact(const double* alphas, const double* us, int n, const Cam& cam, double* mtm) {
+    for (int x = 0; x < 4; ++x)
+        for (int y = x; y < 4; ++y) {
+            double e00 = 0, e02 = 0, e20 = 0, e11 = 0, e12 = 0, e21 = 0, e22 = 0;
+            for (int i = 0; i < n; ++i) {
+                const double ax = alphas[4 * i + x], ay = alphas[4 * i + y];
+                const double du = cam.uc - us[2 * i], dv = cam.vc - us[2 * i + 1];
+                const double x0 = ax * cam.fu, x1 = ax * cam.fv, xu = ax * du, xv = ax * dv;
+                const double y0 = ay * cam.fu, y1 = ay * cam.fv, yu = ay * du, yv = ay * dv;
+                e00 += x0 * y0;
+                e02 += x0 * yu;
+                e20 += xu * y0;
+                e11 += x1 * y1;
+                e12 += x1 * yv;
+                e21 += xv * y1;
+                e22 += xu * yu;
+                e22 += xv * yv;
+            }
+            const double blk[9] = {e00, 0, e02, 0, e11, e12, e20, e21, e22};
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    if (x == y && c < r) continue;   // lower triangle of a diagonal block = mirror of its upper one
+                    mtm[((3 * x + r) * 12 + 3 * y + c) * S] = blk[r * 3 + c];
+                    mtm[((3 * y + c) * 12 + 3 * x + r) * S] = blk[r * 3 + c];
+                }
+        }
 }
 
 P2P_HD inline void compute_ccs(const double* betas, const double* ut8, double ccs[4][3]) {
@@ -545,28 +580,14 @@ P2P_HD inline void camera_point(const double* a, const double ccs[4][3], double*
     for (int j = 0; j < 3; ++j) pc[j] = a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j];
 }
 
-// estimate_R_and_t from the centroids and the 3x3 correlation ABt = sum (pc-pc0)(pw-pw0)^T.
-P2P_HD inline void rt_from_correlation(const double* abt_in, const double* pc0, const double* pw0, double R[3][3], double* t) {
-    double U[9], s[3], V[9];
-    for (int i = 0; i < 9; ++i) U[i] = abt_in[i];
-    jacobi_svd<3, 3>(U, s, V);
-    // complete U to an orthonormal basis when the correlation is rank deficient
-    if (!(s[2] > 1e-14 * s[0])) {
-        if (!(s[1] > 1e-14 * s[0])) {  // rank <= 1: pick any unit vector orthogonal to u0
-            const double ax = fabs(U[0]), ay = fabs(U[3]), az = fabs(U[6]);
-            double e[3] = {0, 0, 0};
-            e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
-            const double d = e[0] * U[0] + e[1] * U[3] + e[2] * U[6];
-            double v1[3] = {e[0] - d * U[0], e[1] - d * U[3], e[2] - d * U[6]};
-            const double nn = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
-            U[1] = v1[0] / nn; U[4] = v1[1] / nn; U[7] = v1[2] / nn;
-        }
-        U[2] = U[3] * U[7] - U[6] * U[4];
-        U[5] = U[6] * U[1] - U[0] * U[7];
-        U[8] = U[0] * U[4] - U[3] * U[1];
-    }
+// estimate_R_and_t from the centroids and the 3x3 correlation ABt = sum (pc-pc0)(pw-pw0)^T:
+// cvSVD(ABt, D, U, V, CV_SVD_MODIFY_A), R = U V^T with the det < 0 fix on the last row.
+P2P_HD inline void rt_from_correlation(const double* abt, const double* pc0, const double* pw0, double R[3][3], double* t) {
+    double w[3], ut[9], vt[9];
+    cv_svd3(abt, w, ut, vt);
+    // U[i][k] = ut[k][i], V[j][k] = vt[k][j]
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[i][j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + U[i * 3 + 2] * V[j * 3 + 2];
+        for (int j = 0; j < 3; ++j) R[i][j] = ut[i] * vt[j] + ut[3 + i] * vt[3 + j] + ut[6 + i] * vt[6 + j];
     const double det = R[0][0] * R[1][1] * R[2][2] + R[0][1] * R[1][2] * R[2][0] + R[0][2] * R[1][0] * R[2][1] -
                        R[0][2] * R[1][1] * R[2][0] - R[0][1] * R[1][0] * R[2][2] - R[0][0] * R[1][2] * R[2][1];
     if (det < 0) { R[2][0] = -R[2][0]; R[2][1] = -R[2][1]; R[2][2] = -R[2][2]; }
@@ -583,12 +604,12 @@ P2P_HD inline double reproj_dist(const double R[3][3], const double* t, const do
 
 // cv::Rodrigues, matrix -> vector (after projecting R onto SO(3) through its SVD) and back.
 P2P_HD inline void rodrigues_to_vec(const double Rin[3][3], double* r) {
-    double U[9], s[3], V[9], R[9];
+    double A[9], w[3], ut[9], vt[9], R[9];
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) U[i * 3 + j] = Rin[i][j];
-    jacobi_svd<3, 3>(U, s, V);
+        for (int j = 0; j < 3; ++j) A[i * 3 + j] = Rin[i][j];
+    cv_svd3(A, w, ut, vt);   // SVD::compute(R, W, U, Vt); R = U*Vt
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[i * 3 + j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + U[i * 3 + 2] * V[j * 3 + 2];
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = ut[i] * vt[j] + ut[3 + i] * vt[3 + j] + ut[6 + i] * vt[6 + j];
     double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
     const double sn = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
     double c = (R[0] + R[4] + R[8] - 1) * 0.5;
@@ -620,20 +641,22 @@ P2P_HD inline void rodrigues_to_mat(const double* r, double R[3][3]) {
     }
     const double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = 1. / theta;
     const double x = r[0] * itheta, y = r[1] * itheta, z = r[2] * itheta;
-    R[0][0] = c + c1 * x * x;     R[0][1] = c1 * x * y - s * z; R[0][2] = c1 * x * z + s * y;
-    R[1][0] = c1 * x * y + s * z; R[1][1] = c + c1 * y * y;     R[1][2] = c1 * y * z - s * x;
-    R[2][0] = c1 * x * z - s * y; R[2][1] = c1 * y * z + s * x; R[2][2] = c + c1 * z * z;
+    R[0][0] = c + c1 * (x * x);       R[0][1] = c1 * (x * y) - s * z; R[0][2] = c1 * (x * z) + s * y;
+    R[1][0] = c1 * (x * y) + s * z; R[1][1] = c + c1 * (y * y);       R[1][2] = c1 * (y * z) - s * x;
+    R[2][0] = c1 * (x * z) - s * y; R[2][1] = c1 * (y * z) + s * x; R[2][2] = c + c1 * (z * z);
 }
 
-// Whole EPnP for a small point set held by one thread (the 5-point RANSAC kernel).
-// pws: n x 3 object points, us: n x 2 pixel coordinates.  Returns the winning R, t.
-template <int MAXN>
-P2P_HD inline void solve_small(const double* pws, const double* us, int n, const Cam& cam, double R[3][3], double* t) {
+// Whole EPnP for a small point set held by one thread (the 5-point RANSAC hypotheses, and refits on <= MAXN inliers),
+// bit-exact with cv2.solvePnP(SOLVEPNP_EPNP) up to libm's sin/cos/acos in Rodrigues.
+// pws: n x 3 object points, us: n x 2 pixel coordinates.  `mtm` = 144-element scratch with element stride S (shared
+// memory on the device).  Returns the winning R, t.
+template <int MAXN, int S = 1>
+P2P_HD inline void solve_small(const double* pws, const double* us, int n, const Cam& cam, double* mtm, double R[3][3], double* t) {
     double cws[4][3], c0[3] = {0, 0, 0}, sc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < 3; ++j) c0[j] += pws[3 * i + j];
     for (int j = 0; j < 3; ++j) c0[j] /= n;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i) {   // cvMulTransposed(PW0, PW0tPW0, 1)
         const double d[3] = {pws[3 * i] - c0[0], pws[3 * i + 1] - c0[1], pws[3 * i + 2] - c0[2]};
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) sc[a * 3 + b] += d[a] * d[b];
@@ -641,17 +664,10 @@ P2P_HD inline void solve_small(const double* pws, const double* us, int n, const
     choose_control_points(c0, sc, n, cws);
     double ci[9], alphas[MAXN * 4];
     control_inverse(cws, ci);
-    double mtm[144];
-    for (int i = 0; i < 144; ++i) mtm[i] = 0.0;
-    for (int i = 0; i < n; ++i) {
-        barycentric(ci, cws, pws + 3 * i, alphas + 4 * i);
-        double m1[12], m2[12];
-        m_rows(alphas + 4 * i, us[2 * i], us[2 * i + 1], cam, m1, m2);
-        for (int a = 0; a < 12; ++a)
-            for (int b = 0; b < 12; ++b) mtm[a * 12 + b] += m1[a] * m1[b] + m2[a] * m2[b];
-    }
-    double ut[48], betas[3][4];   // eigenvectors 8..11 only
-    solve_betas(mtm, cws, ut, betas);
+    for (int i = 0; i < n; ++i) barycentric(ci, cws, pws + 3 * i, alphas + 4 * i);
+    mtm_exact<S>(alphas, us, n, cam, mtm);
+    double ut[48], betas[3][4];   // rows 8..11 of U^T only
+    solve_betas_exact<S>(mtm, cws, ut, betas);
     double best = 0;
     for (int k = 0; k < 3; ++k) {
         double ccs[4][3], pcs[MAXN * 3];

@@ -10,7 +10,8 @@ namespace p2p {
 
 namespace {
 
-constexpr int kHypThreads = 128;
+constexpr int kHypThreads = 192;     // x 144 doubles of shared-memory workspace per thread = 216 KB: one block per SM
+constexpr int kSmallRefit = 32;      // refits on <= this many inliers take the bit-exact serial path
 constexpr int kScoreWarps = 8;
 constexpr int kRefitThreads = 64;   // small blocks: the kernel is dominated by thread 0's serial 12x12 eigen / Gauss-Newton section, so what counts
                                      // is how many problems are resident at once (8 blocks per SM = one wave for 768 problems: 1.17 -> 0.41 ms)
@@ -49,42 +50,49 @@ __device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t,
     return reproj_err_f32(R, t, o, ip, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;
 }
 
-// ---- (1) hypotheses: RNG replay by thread 0, then one 5-point EPnP per thread
-template <int MINB>
-__global__ void __launch_bounds__(kHypThreads, MINB) ransac_hyp_kernel(const PnpProblem* __restrict__ probs,
-                                                                    const float* __restrict__ obj, const float* __restrict__ img,
-                                                                    double* __restrict__ hyp, int iters) {
-    extern __shared__ int s_idx[];
-    const PnpProblem pr = probs[blockIdx.x];
+// ---- (1) hypotheses: one 5-point EPnP per thread, flat over (problem, iteration).  Every thread replays OpenCV's
+// RNG up to its own iteration (<= 100 x 5 draws: noise next to the solver).  The 12x12 M^T M / Jacobi workspace of
+// each thread lives in shared memory, interleaved across the block ([element][thread]: conflict-free, and it is what
+// used to spill into 3.4 KB of local memory per thread).
+__global__ void __launch_bounds__(kHypThreads, 1) ransac_hyp_kernel(const PnpProblem* __restrict__ probs, int n_problems,
+                                                                 const float* __restrict__ obj, const float* __restrict__ img,
+                                                                 double* __restrict__ hyp, int iters) {
+    extern __shared__ double s_ws[];   // [144][kHypThreads]
+    const long long g = static_cast<long long>(blockIdx.x) * kHypThreads + threadIdx.x;
+    const int p = static_cast<int>(g / iters), h = static_cast<int>(g % iters);
+    if (p >= n_problems) return;
+    const PnpProblem pr = probs[p];
     if (pr.n < 6) return;
-    if (threadIdx.x == 0) {
+    int idx[5];
+    {
         CvRng rng;
-        for (int i = 0; i < iters; ++i) ransac_subset5(rng, pr.n, s_idx + 5 * i);
+        for (int i = 0; i <= h; ++i) ransac_subset5(rng, pr.n, idx);
     }
-    __syncthreads();
     const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
     const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
-    for (int h = threadIdx.x; h < iters; h += blockDim.x) {
-        double pws[15], us[10];
-        for (int j = 0; j < 5; ++j) {
-            const long long g = pr.offset + s_idx[5 * h + j];
-            for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(obj[g * 3 + k]);
-            // cv::undistortPoints on CV_32FC2 (no distortion): normalised in double, stored as float32;
-            // epnp::init_points then maps back to pixels in double.
-            const float xn = static_cast<float>((static_cast<double>(img[g * 2]) - pr.uc) * ifx);
-            const float yn = static_cast<float>((static_cast<double>(img[g * 2 + 1]) - pr.vc) * ify);
-            us[2 * j] = static_cast<double>(xn) * pr.fu + pr.uc;
-            us[2 * j + 1] = static_cast<double>(yn) * pr.fv + pr.vc;
-        }
-        double R[3][3], t[3], rv[3];
-        epnp::solve_small<5>(pws, us, 5, cam, R, t);
-        epnp::rodrigues_to_vec(R, rv);   // the RANSAC model is (rvec, tvec) ...
-        epnp::rodrigues_to_mat(rv, R);   // ... and projectPoints turns rvec back into a matrix
-        double* o = hyp + (static_cast<long long>(blockIdx.x) * iters + h) * 12;
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) o[i * 3 + j] = R[i][j];
-        o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
+    double pws[15], us[10];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const long long q = pr.offset + idx[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(obj[q * 3 + k]);
+        // cv::undistortPoints on CV_32FC2 (no distortion): normalised in double, stored as float32;
+        // epnp::init_points then maps back to pixels in double.
+        const float xn = static_cast<float>((static_cast<double>(img[q * 2]) - pr.uc) * ifx);
+        const float yn = static_cast<float>((static_cast<double>(img[q * 2 + 1]) - pr.vc) * ify);
+        us[2 * j] = static_cast<double>(xn) * pr.fu + pr.uc;
+        us[2 * j + 1] = static_cast<double>(yn) * pr.fv + pr.vc;
     }
+    double R[3][3], t[3], rv[3];
+    epnp::solve_small<5, kHypThreads>(pws, us, 5, cam, s_ws + threadIdx.x, R, t);
+    epnp::rodrigues_to_vec(R, rv);   // the RANSAC model is (rvec, tvec) ...
+    epnp::rodrigues_to_mat(rv, R);   // ... and projectPoints turns rvec back into a matrix
+    double* o = hyp + g * 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = R[i][j];
+    o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
 }
 
 // ---- (2) scoring: one warp per hypothesis over the correspondences.  A block stages a tile of kScoreTile
@@ -237,6 +245,49 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         block_reduce<4>(v, s_red, s_sum);
     }
     const int m = static_cast<int>(s_sum[3] + 0.5);
+    const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
+    if (m <= kSmallRefit) {
+        // Few inliers (5 is the minimum the accept rule allows): M^T M is (nearly) rank deficient again and the result
+        // depends on every rounding, so run OpenCV's exact serial operation order on the inliers in index order.
+        __shared__ int s_list[kSmallRefit];
+        __shared__ int s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (int base = 0; base < pr.n; base += blockDim.x) {   // ordered compaction, one block-wide chunk at a time
+            const int i = base + threadIdx.x;
+            const bool f = i < pr.n && mk[i];
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            __shared__ int s_wc[kRefitThreads / 32];
+            if ((threadIdx.x & 31) == 0) s_wc[threadIdx.x >> 5] = __popc(bal);
+            __syncthreads();
+            int off = s_cnt;
+            for (int w = 0; w < (threadIdx.x >> 5); ++w) off += s_wc[w];
+            if (f) s_list[off + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int w = 0; w < kRefitThreads / 32; ++w) s_cnt += s_wc[w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double pws[kSmallRefit * 3], us[kSmallRefit * 2], mtm[144], Rk[3][3], tk[3], rv[3], Rf[3][3];
+            for (int j = 0; j < m; ++j) {
+                const int i = s_list[j];
+                for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(o[3 * i + k]);
+                // solvePnP on the CV_64F inliers: undistortPoints to normalised coordinates (double), back to pixels in epnp
+                us[2 * j] = (static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc;
+                us[2 * j + 1] = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
+            }
+            epnp::solve_small<kSmallRefit, 1>(pws, us, m, cam, mtm, Rk, tk);
+            epnp::rodrigues_to_vec(Rk, rv);
+            epnp::rodrigues_to_mat(rv, Rf);
+            for (int i = 0; i < 3; ++i) {
+                out->rvec[i] = rv[i];
+                out->tvec[i] = tk[i];
+                for (int j = 0; j < 3; ++j) out->R[i * 3 + j] = Rf[i][j];
+            }
+        }
+        return;
+    }
     const double c0[3] = {s_sum[0] / m, s_sum[1] / m, s_sum[2] / m};
     __syncthreads();
     // pass B: scatter matrix PW0^T PW0
@@ -270,7 +321,8 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
                 const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
                 double a[4];
                 epnp::barycentric(s_ci, s_cws, p, a);
-                const double du = pr.uc - static_cast<double>(ip[2 * i]), dv = pr.vc - static_cast<double>(ip[2 * i + 1]);
+                const double du = pr.uc - ((static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc);
+                const double dv = pr.vc - ((static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc);
                 const double q = du * du + dv * dv;
                 int k = 0;
 #pragma unroll
@@ -359,7 +411,8 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
             if (mk[i]) {
                 const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
-                const double u = ip[2 * i], vv = ip[2 * i + 1];
+                const double u = (static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc;
+                const double vv = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[c] += epnp::reproj_dist(s_R[c], s_t[c], p, u, vv, cam);
             }
@@ -408,7 +461,6 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     P2P_CHECK(confidence > 0 && confidence < 1, "confidence must be in (0,1)");
     ensure(n_problems, iters);
     const float thr2 = static_cast<float>(static_cast<double>(reproj_err) * static_cast<double>(reproj_err));
-    static const int hyp_minb = getenv("P2P_HYP_MINB") ? atoi(getenv("P2P_HYP_MINB")) : 3;   // occupancy knob: 3 blocks/SM (168 registers) measured fastest (4.2 -> 3.25 ms per 768 problems)
     static const bool prof = getenv("P2P_PROF_PNP") && atoi(getenv("P2P_PROF_PNP")) != 0;       // per-kernel times to stderr
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     auto mark = [&](int i) {
@@ -417,13 +469,17 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         P2P_CUDA(cudaEventRecord(ev[i], s));
     };
     mark(0);
-    const size_t hyp_smem = iters * 5 * sizeof(int);
-    if (hyp_minb == 3) ransac_hyp_kernel<3><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
-    else if (hyp_minb == 5) ransac_hyp_kernel<5><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
-    else if (hyp_minb == 6) ransac_hyp_kernel<6><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
-    else if (hyp_minb == 8) ransac_hyp_kernel<8><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
-    else if (hyp_minb == 2) ransac_hyp_kernel<2><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
-    else ransac_hyp_kernel<4><<<n_problems, kHypThreads, hyp_smem, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, iters);
+    {
+        const size_t hyp_smem = sizeof(double) * 144 * kHypThreads;
+        static bool attr_set = false;
+        if (!attr_set) {
+            P2P_CUDA(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hyp_smem)));
+            attr_set = true;
+        }
+        const long long total = static_cast<long long>(n_problems) * iters;
+        ransac_hyp_kernel<<<static_cast<unsigned>((total + kHypThreads - 1) / kHypThreads), kHypThreads, hyp_smem, s>>>(
+            problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters);
+    }
     P2P_CUDA(cudaGetLastError());
     mark(1);
     P2P_CHECK(max_n >= 0, "max_n must be the largest correspondence count of the batch");
@@ -443,8 +499,7 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         P2P_CUDA(cudaStreamSynchronize(s));
         float ms[4];
         for (int i = 0; i < 4; ++i) P2P_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-        fprintf(stderr, "pnp[%d problems, minb %d] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, hyp_minb, ms[0], ms[1],
-                ms[2], ms[3]);
+        fprintf(stderr, "pnp[%d problems] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, ms[0], ms[1], ms[2], ms[3]);
         for (auto e : ev) cudaEventDestroy(e);
     }
     launches += 4;

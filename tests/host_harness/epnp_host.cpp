@@ -8,9 +8,9 @@ extern "C" {
 
 void host_epnp_small(const double* pws, const double* us, int n, const double* cam4, double* R9, double* t3) {
     epnp::Cam cam = {cam4[0], cam4[1], cam4[2], cam4[3]};
-    double R[3][3];
-    if (n <= 8) epnp::solve_small<8>(pws, us, n, cam, R, t3);
-    else epnp::solve_small<512>(pws, us, n, cam, R, t3);
+    double R[3][3], mtm[144];
+    if (n <= 8) epnp::solve_small<8>(pws, us, n, cam, mtm, R, t3);
+    else epnp::solve_small<512>(pws, us, n, cam, mtm, R, t3);
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R[i][j];
 }
@@ -36,6 +36,25 @@ void host_eig12(const double* A, double* Vt, double* w) {
     double B[144];
     for (int i = 0; i < 144; ++i) B[i] = A[i];
     epnp::tridiag_eig_sym<12>(B, Vt, w);
+}
+
+// ---- the bit-exact OpenCV linear-algebra restatements, one export per cv2 function they are checked against
+void host_cv_svd12(const double* A, double* w, double* ut, double* vt) {   // cv2.SVDecomp(A) of a 12x12
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j) ut[i * 12 + j] = A[j * 12 + i];
+    epnp::cv_jacobi_svd<12, 12, true, 12>(ut, w, vt);
+}
+void host_cv_svd3(const double* A, double* w, double* ut, double* vt) { epnp::cv_svd3(A, w, ut, vt); }
+void host_cv_invert3(const double* A, double* x) { epnp::cv_invert3_svd(A, x); }                     // cv2.invert(A, DECOMP_SVD)
+void host_cv_solve6(const double* A, const double* b, int n, double* x) {                           // cv2.solve(A, b, DECOMP_SVD)
+    if (n == 3) epnp::cv_solve6_svd<3>(A, b, x);
+    else if (n == 4) epnp::cv_solve6_svd<4>(A, b, x);
+    else epnp::cv_solve6_svd<5>(A, b, x);
+}
+// cv2.mulTransposed(M, aTa=True) of the 2n x 12 matrix epnp::fill_M builds from (alphas, us)
+void host_mtm(const double* alphas, const double* us, int n, const double* cam4, double* mtm) {
+    epnp::Cam cam = {cam4[0], cam4[1], cam4[2], cam4[3]};
+    epnp::mtm_exact(alphas, us, n, cam, mtm);
 }
 }
 
@@ -76,8 +95,8 @@ extern "C" int host_ransac(const double* obj64, const double* img64, int n, cons
             us[2 * j] = (double)xn * cam.fu + cam.uc;
             us[2 * j + 1] = (double)yn * cam.fv + cam.vc;
         }
-        double R[3][3], t[3], rv[3];
-        epnp::solve_small<5>(pws, us, 5, cam, R, t);
+        double R[3][3], t[3], rv[3], mtm[144];
+        epnp::solve_small<5>(pws, us, 5, cam, mtm, R, t);
         epnp::rodrigues_to_vec(R, rv);
         epnp::rodrigues_to_mat(rv, R);
         for (int i = 0; i < 3; ++i)
@@ -101,12 +120,13 @@ extern "C" int host_ransac(const double* obj64, const double* img64, int n, cons
         mask[i] = reproj_err_host(&hyp[best * 12], &hyp[best * 12 + 9], &o[3 * i], &ip[2 * i], cam4) <= thr2;
         if (mask[i]) {
             for (int k = 0; k < 3; ++k) pw.push_back(o[3 * i + k]);
-            uv.push_back(ip[2 * i]); uv.push_back(ip[2 * i + 1]);
+            // solvePnP on CV_64F points: undistortPoints to normalised coordinates in double, epnp maps back to pixels
+            uv.push_back(((double)ip[2 * i] - cam.uc) * (1.0 / cam.fu) * cam.fu + cam.uc);
+            uv.push_back(((double)ip[2 * i + 1] - cam.vc) * (1.0 / cam.fv) * cam.fv + cam.vc);
         }
     }
-    double R[3][3];
-    static thread_local std::vector<char> big;  // solve_small keeps n-sized scratch on the stack
-    epnp::solve_small<20000>(pw.data(), uv.data(), (int)(pw.size() / 3), cam, R, tvec);
+    double R[3][3], mtm[144];
+    epnp::solve_small<20000>(pw.data(), uv.data(), (int)(pw.size() / 3), cam, mtm, R, tvec);   // n-sized scratch on the stack
     epnp::rodrigues_to_vec(R, rvec);
     return max_good;
 }

@@ -25,24 +25,66 @@ def _case(rng, n, noise):
     return np.ascontiguousarray(pw), np.ascontiguousarray(uv)
 
 
-def test_epnp_matches_cv2_solvepnp(host_harness):
-    """n >= 6: identical to cv2.solvePnP(EPNP) to 1e-8 (incl. OpenCV's JacobiSVD sign convention for the
-    control points); n = 5 noise-free: identical; n = 5 noisy: equal up to the null-space basis noise."""
+def test_linear_algebra_bitwise_equals_cv2(host_harness):
+    """The restated OpenCV routines EPnP goes through (csrc/epnp_core.cuh: JacobiSVDImpl_ with OpenCV's own hypot, SVBkSb,
+    MulTransposedR) against the cv2 functions themselves: EVERY output bit equal.  Includes the rank-10 12x12 case of the
+    5-point solver, whose two null-space rows of U are pure rounding residue."""
+    rng = np.random.RandomState(5)
+    for _ in range(40):
+        M = rng.randn(10, 12) * rng.uniform(1, 100)
+        A = np.ascontiguousarray(M.T @ M)
+        w, u, vt = cv2.SVDecomp(A.copy(), flags=cv2.SVD_FULL_UV)
+        W, Ut, Vt = np.zeros(12), np.zeros((12, 12)), np.zeros((12, 12))
+        host_harness.host_cv_svd12(P(A), P(W), P(Ut), P(Vt))
+        assert np.array_equal(w[:, 0], W) and np.array_equal(u.T, Ut) and np.array_equal(vt, Vt)
+    for _ in range(100):
+        A = np.ascontiguousarray(rng.randn(3, 3) * rng.uniform(0.1, 50))
+        if rng.rand() < 0.2:
+            A[:, 2] = 0                                   # exactly rank deficient: the fixed-seed RNG completion path
+        w, u, vt = cv2.SVDecomp(A.copy())
+        W, Ut, Vt = np.zeros(3), np.zeros((3, 3)), np.zeros((3, 3))
+        host_harness.host_cv_svd3(P(A), P(W), P(Ut), P(Vt))
+        assert np.array_equal(w[:, 0], W) and np.array_equal(u.T, Ut) and np.array_equal(vt, Vt)
+        inv = np.zeros((3, 3))
+        host_harness.host_cv_invert3(P(A), P(inv))
+        assert np.array_equal(cv2.invert(A, flags=cv2.DECOMP_SVD)[1], inv)
+    for n in (3, 4, 5):
+        for k in range(60):
+            A = np.ascontiguousarray(rng.randn(6, n) if k % 3 else rng.randn(6, 2) @ rng.randn(2, n))   # full rank / rank 2
+            b = np.ascontiguousarray(rng.randn(6))
+            x = np.zeros(n)
+            host_harness.host_cv_solve6(P(A), P(b), n, P(x))
+            assert np.array_equal(cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_SVD)[1][:, 0], x)
+    for n in (5, 9):
+        for _ in range(20):
+            al, us = np.ascontiguousarray(rng.randn(n, 4)), np.ascontiguousarray(rng.uniform(0, 640, (n, 2)))
+            M = np.zeros((2 * n, 12))                     # epnp::fill_M
+            for i in range(n):
+                for j in range(4):
+                    M[2 * i, 3 * j], M[2 * i, 3 * j + 2] = al[i, j] * CAM[0], al[i, j] * (CAM[2] - us[i, 0])
+                    M[2 * i + 1, 3 * j + 1], M[2 * i + 1, 3 * j + 2] = al[i, j] * CAM[1], al[i, j] * (CAM[3] - us[i, 1])
+            got = np.zeros((12, 12))
+            host_harness.host_mtm(P(al), P(us), n, P(CAM), P(got))
+            assert np.array_equal(cv2.mulTransposed(M, True), got)
+
+
+def test_epnp_bitwise_equals_cv2_solvepnp(host_harness):
+    """The whole EPnP (csrc/epnp_core.cuh solve_small) returns the SAME translation bits as cv2.solvePnP(EPNP) -- also for
+    exactly 5 points, where the solution is a chaotic function of every rounding upstream of the 12x12 SVD -- and the same
+    rotation up to libm's acos/sin/cos in Rodrigues (1e-13)."""
     rng = np.random.RandomState(1)
-    for n in (6, 7, 10, 100, 400):
-        for _ in range(25):
-            pw, uv = _case(rng, n, float(rng.choice([0.5, 2.0, 10.0])))
+    for n in (5, 6, 7, 10, 100, 400):
+        for _ in range(40):
+            pw, uv = _case(rng, n, float(rng.choice([0.0, 0.5, 2.0, 10.0])))
+            pw = pw.astype(np.float32).astype(np.float64)           # what solvePnPRansac hands to the minimal solver
+            uv = uv.astype(np.float32).astype(np.float64)
             ok, rv, tv = cv2.solvePnP(pw.reshape(-1, 1, 3), uv.reshape(-1, 1, 2), K_LM, None, flags=cv2.SOLVEPNP_EPNP)
+            # solvePnP: undistortPoints -> normalised coordinates (double), epnp::init_points maps them back to pixels
+            us = np.ascontiguousarray(((uv - CAM[2:]) * (1.0 / CAM[:2])) * CAM[:2] + CAM[2:])
             R9, t3 = np.zeros(9), np.zeros(3)
-            host_harness.host_epnp_small(P(pw), P(uv), n, P(CAM), P(R9), P(t3))
-            assert np.abs(R9.reshape(3, 3) - cv2.Rodrigues(rv)[0]).max() < 1e-8
-            assert np.abs(t3 - tv[:, 0]).max() < 1e-6
-    for _ in range(25):
-        pw, uv = _case(rng, 5, 0.0)
-        ok, rv, tv = cv2.solvePnP(pw.reshape(-1, 1, 3), uv.reshape(-1, 1, 2), K_LM, None, flags=cv2.SOLVEPNP_EPNP)
-        R9, t3 = np.zeros(9), np.zeros(3)
-        host_harness.host_epnp_small(P(pw), P(uv), 5, P(CAM), P(R9), P(t3))
-        assert np.abs(R9.reshape(3, 3) - cv2.Rodrigues(rv)[0]).max() < 1e-8
+            host_harness.host_epnp_small(P(pw), P(us), n, P(CAM), P(R9), P(t3))
+            assert np.array_equal(t3, tv[:, 0]), (n, t3, tv[:, 0])
+            assert np.abs(R9.reshape(3, 3) - cv2.Rodrigues(rv)[0]).max() < 1e-13
 
 
 def test_rodrigues_roundtrip(host_harness):
@@ -65,17 +107,17 @@ def test_update_num_iters(host_harness):
 
 
 def test_ransac_emulation_matches_cv2_solvepnpransac(host_harness):
-    """The full algorithm of csrc/pnp_ransac.cu (RNG replay, 5-point EPnP, float32 scoring, sequential
-    accept/terminate replay, refit) emulated on the host from the same functions: identical inlier sets to
-    cv2.solvePnPRansac in the large majority of planted cases, tolerance otherwise."""
+    """The full algorithm of csrc/pnp_ransac.cu (RNG replay, 5-point EPnP, float32 scoring, sequential accept/terminate
+    replay, refit) emulated on the host from the same functions: inlier index sets, rvec and tvec IDENTICAL (bit for bit)
+    to cv2.solvePnPRansac in every planted case."""
     import resource
     resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
     rng = np.random.RandomState(0)
-    exact = total = 0
-    for trial in range(24):
+    total = 0
+    for trial in range(60):
         n = int(rng.choice([6, 12, 50, 200, 2000, 8000]))
-        of = float(rng.choice([0, 0.2, 0.4]))
-        pw, uv = _case(rng, n, 1.0)
+        of = float(rng.choice([0, 0.2, 0.4, 0.6]))
+        pw, uv = _case(rng, n, float(rng.choice([0.5, 1.0, 3.0])))
         no = int(n * of)
         idx = rng.choice(n, no, replace=False)
         uv[idx] += rng.uniform(-60, 60, (no, 2))
@@ -88,10 +130,6 @@ def test_ransac_emulation_matches_cv2_solvepnpransac(host_harness):
         if inl is None:
             continue
         total += 1
-        same = np.array_equal(np.nonzero(mask)[0], inl[:, 0])
-        exact += same
-        if same:   # same consensus set -> same refit (up to the null-space noise of very small sets)
-            assert np.abs(rvec - rvc[:, 0]).max() < 1e-5 and np.linalg.norm(tvec - tvc[:, 0]) / np.linalg.norm(tvc) < 1e-5
-        elif n >= 100:
-            assert abs(int(mask.sum()) - len(inl)) <= 0.05 * n and np.abs(rvec - rvc[:, 0]).max() < 2e-2
-    assert exact >= 0.6 * total, (exact, total)
+        assert np.array_equal(np.nonzero(mask)[0], inl[:, 0]), (trial, n, of)
+        assert np.array_equal(rvec, rvc[:, 0]) and np.array_equal(tvec, tvc[:, 0]), (trial, n, of)
+    assert total >= 40

@@ -1,11 +1,11 @@
 """GPU parity of the EPnP-RANSAC kernels against the real cv2.solvePnPRansac (recognition.py:216).
 
-Tolerance, stated up front: OpenCV's RNG, subset draw, acceptance rule, adaptive
-termination and the EPnP refit are replicated; the only non-replicable quantity is the floating-point
-noise that picks the basis of the 2-D null space of the 5-point system, which changes a minority of
-hypotheses at the 1e-3 level.  So: the inlier sets are IDENTICAL in most trials (asserted >= 60 %), and in
-every trial with n >= 100 and >= 50 % planted inliers the rotation differs by <= 0.6 deg, ||dt||/||t|| <= 5e-3
-and the inlier count by <= 5 % of n."""
+Tolerance, stated up front (SURVEY.md section 8c asks for <= 0.1 deg, ||dt||/||t|| <= 1e-3, inlier count within 1 %):
+OpenCV's RNG, subset draw, 5-point EPnP (incl. its own Jacobi SVD, bit for bit -- csrc/epnp_core.cuh), float32 scoring,
+acceptance rule, adaptive termination and the EPnP refit are replicated, so the bar here is much tighter than the
+survey's: the inlier INDEX SETS must be identical to cv2's in every trial (index work: bit-exact), and R|t of the refit on
+those inliers must agree to 1e-6 deg / 1e-9 relative (block-parallel sums instead of OpenCV's sequential ones; refits on
+<= 32 inliers run OpenCV's exact operation order and must agree to 1e-12)."""
 import cv2
 import numpy as np
 import pytest
@@ -29,34 +29,51 @@ def _planted(rng, n, outlier_frac, noise=1.0):
     return pw, uv
 
 
+def _ang(Ra, Rb):
+    return np.degrees(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
 def test_matches_cv2_on_planted_poses():
     from pix2pose_b200.pnp import solve_pnp_ransac
     rng = np.random.RandomState(0)
-    identical = total = 0
-    for trial in range(40):
-        n = int(rng.choice([6, 12, 50, 200, 2000, 8000, 16384]))
-        of = float(rng.choice([0.0, 0.2, 0.4]))
-        pw, uv = _planted(rng, n, of)
+    total = 0
+    for trial in range(60):
+        n = int(rng.choice([6, 7, 12, 50, 200, 2000, 8000, 16384]))
+        of = float(rng.choice([0.0, 0.2, 0.4, 0.6]))
+        pw, uv = _planted(rng, n, of, noise=float(rng.choice([0.5, 1.0, 3.0])))
         ret, rv, tv, inl = cv2.solvePnPRansac(pw, uv.reshape(-1, 1, 2), K_LM, None, flags=cv2.SOLVEPNP_EPNP,
                                               reprojectionError=5, iterationsCount=100)
         g_ret, g_rv, g_tv, g_inl, g_R, _ = solve_pnp_ransac(pw, uv, K_LM, 5.0, 100, 0.99)
-        assert (inl is None) == (g_inl is None)
+        assert (inl is None) == (g_inl is None), (trial, n, of)
         if inl is None:
             continue
         total += 1
-        same = np.array_equal(inl[:, 0], g_inl[:, 0])
-        identical += same
+        assert np.array_equal(inl[:, 0], g_inl[:, 0]), (trial, n, of, len(inl), len(g_inl))     # identical consensus set
         Rcv = cv2.Rodrigues(rv)[0]
-        ang = np.degrees(np.arccos(np.clip((np.trace(Rcv.T @ g_R) - 1) / 2, -1, 1)))
-        dt = np.linalg.norm(g_tv - tv) / np.linalg.norm(tv)
-        if same and len(inl) >= 12:
-            assert ang < 1e-4 and dt < 1e-8                 # same inliers -> same refit (a 5/6-point refit keeps the
-            #                                                 null-space ambiguity described above)
-        if n >= 100:
-            assert ang <= 0.6 and dt <= 5e-3, (trial, n, of, ang, dt)
-            assert abs(len(inl) - len(g_inl)) <= 0.05 * n
+        ang, dt = _ang(Rcv, g_R), np.linalg.norm(g_tv - tv) / np.linalg.norm(tv)
+        if len(inl) <= 32:
+            assert np.abs(g_rv - rv).max() <= 1e-12 and dt <= 1e-12, (trial, n, len(inl), np.abs(g_rv - rv).max(), dt)
+        else:
+            assert ang <= 1e-6 and dt <= 1e-9, (trial, n, of, ang, dt)
         assert np.allclose(cv2.Rodrigues(g_rv)[0], g_R, atol=1e-12)     # R = Rodrigues(rvec), recognition.py:223
-    assert identical >= 0.6 * total, (identical, total)
+    assert total >= 40
+
+
+def test_hypotheses_replay_cv2_on_hard_cases():
+    """Low inlier ratios and heavy noise make RANSAC run all 100 iterations and accept late hypotheses: every accepted
+    model along the way must have been scored exactly like OpenCV's for the final consensus set to coincide."""
+    from pix2pose_b200.pnp import solve_pnp_ransac
+    rng = np.random.RandomState(5)
+    for trial in range(30):
+        n = int(rng.choice([100, 400, 1500, 5000]))
+        pw, uv = _planted(rng, n, float(rng.choice([0.7, 0.8])), noise=float(rng.choice([1.0, 2.0, 4.0])))
+        pw[:, 2] = np.round(pw[:, 2])                       # quantised coordinate -> occasional exactly coplanar 5-subsets
+        ret, rv, tv, inl = cv2.solvePnPRansac(pw, uv.reshape(-1, 1, 2), K_LM, None, flags=cv2.SOLVEPNP_EPNP,
+                                              reprojectionError=5, iterationsCount=100)
+        g = solve_pnp_ransac(pw, uv, K_LM, 5.0, 100, 0.99)
+        assert (inl is None) == (g[3] is None), trial
+        if inl is not None:
+            assert np.array_equal(inl[:, 0], g[3][:, 0]), (trial, n, len(inl), len(g[3]))
 
 
 def test_edge_cases():
@@ -71,7 +88,7 @@ def test_edge_cases():
     g = solve_pnp_ransac(pw, uv, K_LM)
     assert (inl is None) == (g[3] is None)
     if inl is not None:
-        assert abs(len(inl) - len(g[3])) <= 6
+        assert np.array_equal(inl[:, 0], g[3][:, 0])
     # all points identical in the image (degenerate): must not hang or produce NaN counts
     pw, uv = _planted(rng, 100, 0.0)
     uv[:] = uv[0]
