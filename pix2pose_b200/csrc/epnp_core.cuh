@@ -186,25 +186,38 @@ P2P_HD inline double cv_hypot(double a, double b) {   // lapack.cpp's local hypo
 
 // JacobiSVDImpl_<double>: one-sided Jacobi on the N rows (length M) of At.  On return W = singular values
 // (descending), rows i < N1 of At scaled to unit length (= rows of U^T), Vt (if WANT_V) = V^T.
+// On the device every instance (3x3, 6x3, 6x4, 6x5) is fully unrolled over rows, pairs and columns (only the sweep loop
+// stays a loop; the descending selection sort swaps under a predicate instead of through a computed row index), so
+// At / Vt / W are only ever indexed statically and live in registers rather than in local memory.
+#if defined(__CUDACC__)
+#define P2P_UNROLL _Pragma("unroll")
+#else
+#define P2P_UNROLL
+#endif
 template <int M, int N, bool WANT_V, int N1, int S = 1>
 P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
     const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
 #define P2P_AT(i, k) At[((i) * M + (k)) * S]
+    P2P_UNROLL
     for (int i = 0; i < N; ++i) {
         double sd = 0;
+        P2P_UNROLL
         for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
         W[i] = sd;
         if (WANT_V) {
-            for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
-            Vt[i * N + i] = 1;
+            P2P_UNROLL
+            for (int k = 0; k < N; ++k) Vt[i * N + k] = (k == i) ? 1 : 0;
         }
     }
     const int max_iter = M > 30 ? M : 30;
     for (int iter = 0; iter < max_iter; ++iter) {
         bool changed = false;
-        for (int i = 0; i < N - 1; ++i)
+        P2P_UNROLL
+        for (int i = 0; i < N - 1; ++i) {
+            P2P_UNROLL
             for (int j = i + 1; j < N; ++j) {
                 double a = W[i], p = 0, b = W[j];
+                P2P_UNROLL
                 for (int k = 0; k < M; ++k) p += P2P_AT(i, k) * P2P_AT(j, k);
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
@@ -219,6 +232,7 @@ P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+                P2P_UNROLL
                 for (int k = 0; k < M; ++k) {
                     const double x = P2P_AT(i, k), y = P2P_AT(j, k);
                     const double t0 = c * x + s * y;
@@ -231,18 +245,147 @@ P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
                 W[i] = a;
                 W[j] = b;
                 changed = true;
-                if (WANT_V)
+                if (WANT_V) {
+                    P2P_UNROLL
                     for (int k = 0; k < N; ++k) {
                         const double x = Vt[i * N + k], y = Vt[j * N + k];
                         Vt[i * N + k] = c * x + s * y;
                         Vt[j * N + k] = -s * x + c * y;
                     }
+                }
             }
+        }
+        if (!changed) break;
+    }
+    P2P_UNROLL
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        P2P_UNROLL
+        for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    P2P_UNROLL
+    for (int i = 0; i < N - 1; ++i) {   // selection sort, descending: j = first maximum of W[i..]
+        int j = i;
+        double wj = W[i];
+        P2P_UNROLL
+        for (int k = i + 1; k < N; ++k)
+            if (wj < W[k]) { j = k; wj = W[k]; }
+        P2P_UNROLL
+        for (int jj = i + 1; jj < N; ++jj)
+            if (j == jj) {
+                const double tw = W[i]; W[i] = W[jj]; W[jj] = tw;
+                P2P_UNROLL
+                for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(jj, k); P2P_AT(jj, k) = t; }
+                if (WANT_V) {
+                    P2P_UNROLL
+                    for (int k = 0; k < N; ++k) { const double t = Vt[i * N + k]; Vt[i * N + k] = Vt[jj * N + k]; Vt[jj * N + k] = t; }
+                }
+            }
+    }
+    // unit rows; a singular value <= DBL_MIN gets a vector regenerated from the fixed-seed RNG and orthogonalised
+    // against the previous rows (exactly rank-deficient input, e.g. coplanar points with one coordinate constant)
+    unsigned long long rng = 0x12345678ull;
+    P2P_UNROLL
+    for (int i = 0; i < N1; ++i) {
+        double sd = W[i];
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / M;
+            P2P_UNROLL
+            for (int k = 0; k < M; ++k) {
+                rng = (unsigned long long)(unsigned)rng * 4164903690ull + (unsigned)(rng >> 32);
+                P2P_AT(i, k) = ((unsigned)rng & 256) != 0 ? val0 : -val0;
+            }
+            for (int it = 0; it < 2; ++it) {
+                P2P_UNROLL
+                for (int j = 0; j < i; ++j) {
+                    sd = 0;
+                    P2P_UNROLL
+                    for (int k = 0; k < M; ++k) sd += P2P_AT(i, k) * P2P_AT(j, k);
+                    double asum = 0;
+                    P2P_UNROLL
+                    for (int k = 0; k < M; ++k) {
+                        const double t = P2P_AT(i, k) - sd * P2P_AT(j, k);
+                        P2P_AT(i, k) = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    P2P_UNROLL
+                    for (int k = 0; k < M; ++k) P2P_AT(i, k) *= asum;
+                }
+            }
+            sd = 0;
+            P2P_UNROLL
+            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+            sd = sqrt(sd);
+        }
+        const double sc = sd > minval ? 1 / sd : 0.;
+        P2P_UNROLL
+        for (int k = 0; k < M; ++k) P2P_AT(i, k) *= sc;
+    }
+#undef P2P_AT
+}
+
+// The same routine specialised for what EPnP asks of the 12 x 12 M^T M (U^T only), laid out for a GPU thread: row i
+// stays in registers while it is paired with rows i+1.., and the squared row norms W[] are not kept in memory at all --
+// OpenCV's W[i] is by construction the k-ordered sum of squares of the row as stored, so recomputing it next to the dot
+// product (three independent add chains) gives the same bits and removes a dynamically indexed array (= local memory)
+// from the inner loop.  Bitwise identical to cv_jacobi_svd<12, 12, false, 12> (tests/test_epnp_host.py).
+template <int S = 1>
+P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
+    const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
+    constexpr int N = 12;
+#define P2P_AT(i, k) At[((i) * N + (k)) * S]
+    for (int iter = 0; iter < 30; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; ++i) {
+            double ri[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) ri[k] = P2P_AT(i, k);
+            bool dirty = false;
+            for (int j = i + 1; j < N; ++j) {
+                double rj[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) rj[k] = P2P_AT(j, k);
+                double a = 0, b = 0, p = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    a += ri[k] * ri[k];
+                    b += rj[k] * rj[k];
+                    p += ri[k] * rj[k];
+                }
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = cv_hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double x = ri[k], y = rj[k];
+                    ri[k] = c * x + s * y;
+                    P2P_AT(j, k) = -s * x + c * y;
+                }
+                dirty = true;
+            }
+            if (dirty) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) P2P_AT(i, k) = ri[k];
+                changed = true;
+            }
+        }
         if (!changed) break;
     }
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-        for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
         W[i] = sqrt(sd);
     }
     for (int i = 0; i < N - 1; ++i) {
@@ -251,41 +394,38 @@ P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
             if (W[j] < W[k]) j = k;
         if (i != j) {
             const double tw = W[i]; W[i] = W[j]; W[j] = tw;
-            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(j, k); P2P_AT(j, k) = t; }
-            if (WANT_V)
-                for (int k = 0; k < N; ++k) { const double t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+            for (int k = 0; k < N; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(j, k); P2P_AT(j, k) = t; }
         }
     }
-    // unit rows; a singular value <= DBL_MIN gets a vector regenerated from the fixed-seed RNG and orthogonalised
-    // against the previous rows (exactly rank-deficient input, e.g. coplanar points with one coordinate constant)
     unsigned long long rng = 0x12345678ull;
-    for (int i = 0; i < N1; ++i) {
+    for (int i = 0; i < N; ++i) {
         double sd = W[i];
-        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
-            const double val0 = 1. / M;
-            for (int k = 0; k < M; ++k) {
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {   // exactly zero singular value: see cv_jacobi_svd
+            const double val0 = 1. / N;
+            for (int k = 0; k < N; ++k) {
                 rng = (unsigned long long)(unsigned)rng * 4164903690ull + (unsigned)(rng >> 32);
                 P2P_AT(i, k) = ((unsigned)rng & 256) != 0 ? val0 : -val0;
             }
             for (int it = 0; it < 2; ++it)
                 for (int j = 0; j < i; ++j) {
                     sd = 0;
-                    for (int k = 0; k < M; ++k) sd += P2P_AT(i, k) * P2P_AT(j, k);
+                    for (int k = 0; k < N; ++k) sd += P2P_AT(i, k) * P2P_AT(j, k);
                     double asum = 0;
-                    for (int k = 0; k < M; ++k) {
+                    for (int k = 0; k < N; ++k) {
                         const double t = P2P_AT(i, k) - sd * P2P_AT(j, k);
                         P2P_AT(i, k) = t;
                         asum += fabs(t);
                     }
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    for (int k = 0; k < M; ++k) P2P_AT(i, k) *= asum;
+                    for (int k = 0; k < N; ++k) P2P_AT(i, k) *= asum;
                 }
             sd = 0;
-            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
+            for (int k = 0; k < N; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
             sd = sqrt(sd);
         }
         const double sc = sd > minval ? 1 / sd : 0.;
-        for (int k = 0; k < M; ++k) P2P_AT(i, k) *= sc;
+#pragma unroll
+        for (int k = 0; k < N; ++k) P2P_AT(i, k) *= sc;
     }
 #undef P2P_AT
 }
@@ -530,7 +670,7 @@ P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8,
 template <int S = 1>
 P2P_HD inline void solve_betas_exact(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
     double w[12];
-    cv_jacobi_svd<12, 12, false, 12, S>(mtm, w, nullptr);   // MtM is bitwise symmetric, so A^T = A
+    cv_jacobi_svd12_ut<S>(mtm, w);   // MtM is bitwise symmetric, so A^T = A
     for (int i = 0; i < 48; ++i) ut8[i] = mtm[(96 + i) * S];
     betas_from_ut(ut8, cws, betas);
 }
@@ -644,6 +784,61 @@ P2P_HD inline void rodrigues_to_mat(const double* r, double R[3][3]) {
     R[0][0] = c + c1 * (x * x);       R[0][1] = c1 * (x * y) - s * z; R[0][2] = c1 * (x * z) + s * y;
     R[1][0] = c1 * (x * y) + s * z; R[1][1] = c + c1 * (y * y);       R[1][2] = c1 * (y * z) - s * x;
     R[2][0] = c1 * (x * z) - s * y; R[2][1] = c1 * (y * z) + s * x; R[2][2] = c + c1 * (z * z);
+}
+
+// Large-n refit (csrc/pnp_ransac.cu epnp_refit_kernel): everything EPnP needs from the n inliers are 52 sums, taken by a
+// block reduction --
+//   s[k], s[10+k], s[20+k], s[30+k], k = pair (x <= y) of control points: sum of a_x a_y {1, du, dv, du^2 + dv^2}
+//   (du = uc - u, dv = vc - v): M^T M in structured form;   s[40 + 3j + c] = sum a_j (pw_c - c0_c): correlation terms.
+// This serial tail turns them into the three candidate poses.  pf = first inlier (solve_for_sign looks at point 0).
+P2P_HD inline void refit_candidates(const double* s, int m, const double* c0, const double cws[4][3], const double* ci, const Cam& cam,
+                                    const double* pf, double Rs[3][3][3], double ts[3][3]) {
+    double mtm[144], ut[48], betas[3][4];
+    int k = 0;
+    for (int x = 0; x < 4; ++x)
+        for (int y = x; y < 4; ++y) {
+            const double S = s[k], Su = s[10 + k], Sv = s[20 + k], Sq = s[30 + k];
+            const double blk[9] = {cam.fu * cam.fu * S, 0, cam.fu * Su, 0, cam.fv * cam.fv * S, cam.fv * Sv, cam.fu * Su, cam.fv * Sv, Sq};
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    mtm[(3 * x + r) * 12 + 3 * y + c] = blk[r * 3 + c];
+                    mtm[(3 * y + c) * 12 + 3 * x + r] = blk[r * 3 + c];
+                }
+            ++k;
+        }
+    solve_betas(mtm, cws, ut, betas);
+    double af[4];
+    barycentric(ci, cws, pf, af);
+    // S_j = sum_i alpha_ij: alpha sums to 1 per point, so it is the row sum of the pair table
+    double Srow[4] = {0, 0, 0, 0};
+    k = 0;
+    for (int x = 0; x < 4; ++x)
+        for (int y = x; y < 4; ++y) {
+            Srow[x] += s[k];
+            if (y != x) Srow[y] += s[k];
+            ++k;
+        }
+    double dsum[3] = {0, 0, 0};   // sum (pw - c0): ~0 (rounding only), kept for fidelity
+    for (int j = 0; j < 4; ++j)
+        for (int q = 0; q < 3; ++q) dsum[q] += s[40 + j * 3 + q];
+    for (int c = 0; c < 3; ++c) {
+        double ccs[4][3], pc[3];
+        compute_ccs(betas[c], ut, ccs);
+        camera_point(af, ccs, pc);
+        const double sg = pc[2] < 0.0 ? -1.0 : 1.0;
+        // alphas are affine in pw:  pc0 = sum_j (S_j / m) ccs_j,  pw0 = c0,  ABt = sum_j ccs_j T_j^T - pc0 (x) sum(pw - c0)
+        double pc0[3] = {0, 0, 0}, abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 4; ++j)
+            for (int r = 0; r < 3; ++r) ccs[j][r] *= sg;
+        for (int j = 0; j < 4; ++j)
+            for (int r = 0; r < 3; ++r) pc0[r] += Srow[j] / m * ccs[j][r];
+        for (int j = 0; j < 4; ++j)
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s[40 + j * 3 + q];
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * dsum[q];
+        rt_from_correlation(abt, pc0, c0, Rs[c], ts[c]);
+    }
 }
 
 // Whole EPnP for a small point set held by one thread (the 5-point RANSAC hypotheses, and refits on <= MAXN inliers),

@@ -11,7 +11,6 @@ namespace p2p {
 namespace {
 
 constexpr int kHypThreads = 192;     // x 144 doubles of shared-memory workspace per thread = 216 KB: one block per SM
-constexpr int kSmallRefit = 32;      // refits on <= this many inliers take the bit-exact serial path
 constexpr int kScoreWarps = 8;
 constexpr int kRefitThreads = 64;   // small blocks: the kernel is dominated by thread 0's serial 12x12 eigen / Gauss-Newton section, so what counts
                                      // is how many problems are resident at once (8 blocks per SM = one wave for 768 problems: 1.17 -> 0.41 ms)
@@ -141,14 +140,15 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
 __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __restrict__ probs, const float* __restrict__ obj,
                                                             const float* __restrict__ img, const double* __restrict__ hyp,
                                                             const int* __restrict__ counts, int* __restrict__ best,
-                                                            uint8_t* __restrict__ mask, PnpResult* __restrict__ res,
+                                                            uint8_t* __restrict__ mask, int* __restrict__ small_list,
+                                                            PnpResult* __restrict__ res,
                                                             int iters, float thr2, double confidence) {
     __shared__ int s_best;
     const PnpProblem pr = probs[blockIdx.x];
     PnpResult* out = res + blockIdx.x;
     if (pr.n < 6) {
         if (threadIdx.x == 0) {
-            out->status = -1; out->n_inliers = -1; out->best_iter = -1; out->iters_run = 0;
+            out->status = -1; out->n_inliers = -1; out->best_iter = -1; out->iters_run = 0; out->n_mask = 0;
             best[2 * blockIdx.x] = -1; best[2 * blockIdx.x + 1] = 0;
         }
         return;
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
     uint8_t* mk = mask + pr.offset;
     if (b < 0) {
         for (int i = threadIdx.x; i < pr.n; i += blockDim.x) mk[i] = 0;
+        if (threadIdx.x == 0) out->n_mask = 0;
         return;
     }
     const double* m = hyp + (static_cast<long long>(blockIdx.x) * iters + b) * 12;
@@ -184,11 +185,69 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
     t[0] = m[9]; t[1] = m[10]; t[2] = m[11];
     const float* o = obj + pr.offset * 3;
     const float* ip = img + pr.offset * 2;
-    for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
-        mk[i] = reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2 ? 1 : 0;
+    // Inlier mask; when the consensus set is small (<= kSmallRefit) also its indices in ascending order, for the
+    // exact serial refit (ordered compaction: ballot + running block offset, one 256-wide chunk at a time).
+    __shared__ int s_wc[8], s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int* list = small_list + blockIdx.x * kSmallRefit;
+    for (int base = 0; base < pr.n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool f = i < pr.n && reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;
+        if (i < pr.n) mk[i] = f ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if ((threadIdx.x & 31) == 0) s_wc[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        int off = s_cnt;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) off += s_wc[w];
+        off += __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+        if (f && off < kSmallRefit) list[off] = i;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 0; w < 8; ++w) s_cnt += s_wc[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out->n_mask = s_cnt;
 }
 
-// ---- (4) EPnP on all inliers (double), one CTA per problem
+// ---- (4a) refit on a small consensus set (5 is the minimum the accept rule allows): M^T M is (nearly) rank deficient
+// again and the result depends on every rounding, so one thread per problem runs OpenCV's exact serial operation order
+// on the inliers in index order (solve_small, the routine of the hypothesis kernel; workspace in shared memory).
+constexpr int kSmallThreads = 32;
+__global__ void __launch_bounds__(kSmallThreads) epnp_refit_small_kernel(const PnpProblem* __restrict__ probs, int n_problems,
+                                                                        const float* __restrict__ obj, const float* __restrict__ img,
+                                                                        const int* __restrict__ small_list, PnpResult* __restrict__ res) {
+    __shared__ double s_ws[144 * kSmallThreads];
+    const int p = blockIdx.x * kSmallThreads + threadIdx.x;
+    if (p >= n_problems) return;
+    const PnpProblem pr = probs[p];
+    PnpResult* out = res + p;
+    if (pr.n < 6 || out->status != 1 || out->n_mask > kSmallRefit) return;
+    const int m = out->n_mask;
+    const float* o = obj + pr.offset * 3;
+    const float* ip = img + pr.offset * 2;
+    const int* list = small_list + p * kSmallRefit;
+    const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
+    const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
+    double pws[kSmallRefit * 3], us[kSmallRefit * 2], Rk[3][3], tk[3], rv[3], Rf[3][3];
+    for (int j = 0; j < m; ++j) {
+        const int i = list[j];
+        for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(o[3 * i + k]);
+        // solvePnP on the CV_64F inliers: undistortPoints to normalised coordinates (double), back to pixels in epnp
+        us[2 * j] = (static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc;
+        us[2 * j + 1] = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
+    }
+    epnp::solve_small<kSmallRefit, kSmallThreads>(pws, us, m, cam, s_ws + threadIdx.x, Rk, tk);
+    epnp::rodrigues_to_vec(Rk, rv);
+    epnp::rodrigues_to_mat(rv, Rf);
+    for (int i = 0; i < 3; ++i) {
+        out->rvec[i] = rv[i];
+        out->tvec[i] = tk[i];
+        for (int j = 0; j < 3; ++j) out->R[i * 3 + j] = Rf[i][j];
+    }
+}
+
+// ---- (4b) EPnP on all inliers (double) of a larger consensus set, one CTA per problem
 template <int NV>
 __device__ __forceinline__ void block_reduce(double* v, double* s_red, double* s_out) {
     // v[NV] per thread -> s_out[NV] block sums
@@ -214,7 +273,7 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
                                                                    const uint8_t* __restrict__ mask, PnpResult* __restrict__ res) {
     __shared__ double s_red[(kRefitThreads / 32) * 52];
     __shared__ double s_sum[52];
-    __shared__ double s_cws[4][3], s_ci[9], s_ccs[3][4][3], s_R[3][3][3], s_t[3][3];
+    __shared__ double s_cws[4][3], s_ci[9], s_R[3][3][3], s_t[3][3];
     __shared__ int s_first;
     const PnpProblem pr = probs[blockIdx.x];
     PnpResult* out = res + blockIdx.x;
@@ -225,6 +284,7 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         }
         return;
     }
+    if (out->n_mask <= kSmallRefit) return;   // epnp_refit_small_kernel's case
     const float* o = obj + pr.offset * 3;
     const float* ip = img + pr.offset * 2;
     const uint8_t* mk = mask + pr.offset;
@@ -246,48 +306,6 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
     }
     const int m = static_cast<int>(s_sum[3] + 0.5);
     const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
-    if (m <= kSmallRefit) {
-        // Few inliers (5 is the minimum the accept rule allows): M^T M is (nearly) rank deficient again and the result
-        // depends on every rounding, so run OpenCV's exact serial operation order on the inliers in index order.
-        __shared__ int s_list[kSmallRefit];
-        __shared__ int s_cnt;
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-        for (int base = 0; base < pr.n; base += blockDim.x) {   // ordered compaction, one block-wide chunk at a time
-            const int i = base + threadIdx.x;
-            const bool f = i < pr.n && mk[i];
-            const unsigned bal = __ballot_sync(0xffffffffu, f);
-            __shared__ int s_wc[kRefitThreads / 32];
-            if ((threadIdx.x & 31) == 0) s_wc[threadIdx.x >> 5] = __popc(bal);
-            __syncthreads();
-            int off = s_cnt;
-            for (int w = 0; w < (threadIdx.x >> 5); ++w) off += s_wc[w];
-            if (f) s_list[off + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = i;
-            __syncthreads();
-            if (threadIdx.x == 0)
-                for (int w = 0; w < kRefitThreads / 32; ++w) s_cnt += s_wc[w];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            double pws[kSmallRefit * 3], us[kSmallRefit * 2], mtm[144], Rk[3][3], tk[3], rv[3], Rf[3][3];
-            for (int j = 0; j < m; ++j) {
-                const int i = s_list[j];
-                for (int k = 0; k < 3; ++k) pws[3 * j + k] = static_cast<double>(o[3 * i + k]);
-                // solvePnP on the CV_64F inliers: undistortPoints to normalised coordinates (double), back to pixels in epnp
-                us[2 * j] = (static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc;
-                us[2 * j + 1] = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
-            }
-            epnp::solve_small<kSmallRefit, 1>(pws, us, m, cam, mtm, Rk, tk);
-            epnp::rodrigues_to_vec(Rk, rv);
-            epnp::rodrigues_to_mat(rv, Rf);
-            for (int i = 0; i < 3; ++i) {
-                out->rvec[i] = rv[i];
-                out->tvec[i] = tk[i];
-                for (int j = 0; j < 3; ++j) out->R[i * 3 + j] = Rf[i][j];
-            }
-        }
-        return;
-    }
     const double c0[3] = {s_sum[0] / m, s_sum[1] / m, s_sum[2] / m};
     __syncthreads();
     // pass B: scatter matrix PW0^T PW0
@@ -341,68 +359,10 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         block_reduce<52>(v, s_red, s_sum);
     }
     if (threadIdx.x == 0) {
-        double mtm[144], ut[48], betas[3][4];
-        int k = 0;
-        for (int x = 0; x < 4; ++x)
-            for (int y = x; y < 4; ++y) {
-                const double S = s_sum[k], Su = s_sum[10 + k], Sv = s_sum[20 + k], Sq = s_sum[30 + k];
-                const double blk[9] = {pr.fu * pr.fu * S, 0, pr.fu * Su, 0, pr.fv * pr.fv * S, pr.fv * Sv, pr.fu * Su, pr.fv * Sv, Sq};
-                for (int r = 0; r < 3; ++r)
-                    for (int c = 0; c < 3; ++c) {
-                        mtm[(3 * x + r) * 12 + 3 * y + c] = blk[r * 3 + c];
-                        mtm[(3 * y + c) * 12 + 3 * x + r] = blk[r * 3 + c];
-                    }
-                ++k;
-            }
-        epnp::solve_betas(mtm, s_cws, ut, betas);
         // sign reference: camera-frame z of the first inlier (epnp.cpp solve_for_sign uses pcs[2])
         const int f = s_first;
         const double pf[3] = {o[3 * f], o[3 * f + 1], o[3 * f + 2]};
-        double af[4];
-        epnp::barycentric(s_ci, s_cws, pf, af);
-        for (int c = 0; c < 3; ++c) {
-            double ccs[4][3], pc[3];
-            epnp::compute_ccs(betas[c], ut, ccs);
-            epnp::camera_point(af, ccs, pc);
-            const double sg = pc[2] < 0.0 ? -1.0 : 1.0;
-            // pc0 = sum_j mean(alpha_j) ccs_j and ABt = sum_j ccs_j T_j^T - m pc0 (pw0 - c0)^T; alphas are
-            // affine in pw, so with S_j = sum alpha_j:  pc0 = sum_j (S_j/m) ccs_j ; pw0 = c0 exactly.
-            double pc0[3] = {0, 0, 0}, abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int j = 0; j < 4; ++j)
-                for (int r = 0; r < 3; ++r) {
-                    ccs[j][r] *= sg;
-                    s_ccs[c][j][r] = ccs[j][r];
-                }
-            // S_j = sum_i alpha_ij = sum over pairs containing j ... alpha sums to 1 per point, so
-            // sum_i alpha_ij = sum_y sum_i alpha_ij alpha_iy = row sums of the pair table.
-            double Srow[4] = {0, 0, 0, 0};
-            {
-                int kk = 0;
-                for (int x = 0; x < 4; ++x)
-                    for (int y = x; y < 4; ++y) {
-                        Srow[x] += s_sum[kk];
-                        if (y != x) Srow[y] += s_sum[kk];
-                        ++kk;
-                    }
-            }
-            for (int j = 0; j < 4; ++j)
-                for (int r = 0; r < 3; ++r) pc0[r] += Srow[j] / m * ccs[j][r];
-            for (int j = 0; j < 4; ++j)
-                for (int r = 0; r < 3; ++r)
-                    for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s_sum[40 + j * 3 + q];
-            // subtract pc0 (x) sum(pw - c0); the latter is ~0 (rounding only) but kept for fidelity
-            double dsum[3] = {0, 0, 0};
-            for (int j = 0; j < 4; ++j)
-                for (int q = 0; q < 3; ++q) dsum[q] += s_sum[40 + j * 3 + q];
-            for (int r = 0; r < 3; ++r)
-                for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * dsum[q];
-            double Rk[3][3], tk[3];
-            epnp::rt_from_correlation(abt, pc0, c0, Rk, tk);
-            for (int r = 0; r < 3; ++r) {
-                s_t[c][r] = tk[r];
-                for (int q = 0; q < 3; ++q) s_R[c][r][q] = Rk[r][q];
-            }
-        }
+        epnp::refit_candidates(s_sum, m, c0, s_cws, s_ci, cam, pf, s_R, s_t);
     }
     __syncthreads();
     // pass E: mean reprojection distance of each of the three candidates
@@ -450,6 +410,7 @@ void PnpSolver::ensure(int n_problems, int iters) {
         hyp_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_ * 12);
         counts_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_);
         best_.alloc(static_cast<size_t>(cap_problems_) * 2);
+        small_.alloc(static_cast<size_t>(cap_problems_) * kSmallRefit);
     }
 }
 
@@ -489,9 +450,12 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     P2P_CUDA(cudaGetLastError());
     mark(2);
     ransac_select_kernel<<<n_problems, 256, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, best_.p, mask_dev,
-                                                    results_dev, iters, thr2, confidence);
+                                                    small_.p, results_dev, iters, thr2, confidence);
     P2P_CUDA(cudaGetLastError());
     mark(3);
+    epnp_refit_small_kernel<<<(n_problems + kSmallThreads - 1) / kSmallThreads, kSmallThreads, 0, s>>>(problems_dev, n_problems, obj_dev,
+                                                                                                       img_dev, small_.p, results_dev);
+    P2P_CUDA(cudaGetLastError());
     epnp_refit_kernel<<<n_problems, kRefitThreads, 0, s>>>(problems_dev, obj_dev, img_dev, mask_dev, results_dev);
     P2P_CUDA(cudaGetLastError());
     mark(4);
@@ -502,7 +466,7 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         fprintf(stderr, "pnp[%d problems] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, ms[0], ms[1], ms[2], ms[3]);
         for (auto e : ev) cudaEventDestroy(e);
     }
-    launches += 4;
+    launches += 5;
 }
 
 void PnpSolver::solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,

@@ -32,7 +32,11 @@ struct PnpResult {
     int best_iter;                  // iteration whose hypothesis won
     int iters_run;                  // iterations OpenCV's adaptive loop would have executed
     int status;                     // 1 ok, 0 no consensus, -1 too few points
+    int n_mask;                     // inliers counted while writing the mask (== n_inliers when status is 1)
+    int pad;
 };
+
+constexpr int kSmallRefit = 32;     // consensus sets up to this size are refitted in OpenCV's exact serial operation order
 
 class PnpSolver {
   public:
@@ -52,6 +56,7 @@ class PnpSolver {
     DevBuf<double> hyp_;   // [problems][iters][12]
     DevBuf<int> counts_;   // [problems][iters]
     DevBuf<int> best_;     // [problems][2]
+    DevBuf<int> small_;    // [problems][kSmallRefit] ascending inlier indices of small consensus sets
     int cap_problems_ = 0, cap_iters_ = 0;
     cudaStream_t stream_ = nullptr;
     DevBuf<float> h_obj_, h_img_;

@@ -56,6 +56,45 @@ void host_mtm(const double* alphas, const double* us, int n, const double* cam4,
     epnp::Cam cam = {cam4[0], cam4[1], cam4[2], cam4[3]};
     epnp::mtm_exact(alphas, us, n, cam, mtm);
 }
+// Host emulation of epnp_refit_kernel's large-n path: the 52 structured sums (taken sequentially here, by a block
+// reduction on the device), then the same serial tail (epnp::refit_candidates) and candidate choice.
+void host_refit_large(const double* pws, const double* us, int n, const double* cam4, double* rvec, double* t3) {
+    epnp::Cam cam = {cam4[0], cam4[1], cam4[2], cam4[3]};
+    double c0[3] = {0, 0, 0}, sc[9] = {0}, cws[4][3], ci[9], s[52] = {0};
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 3; ++j) c0[j] += pws[3 * i + j];
+    for (int j = 0; j < 3; ++j) c0[j] /= n;
+    for (int i = 0; i < n; ++i) {
+        const double d[3] = {pws[3 * i] - c0[0], pws[3 * i + 1] - c0[1], pws[3 * i + 2] - c0[2]};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) sc[a * 3 + b] += d[a] * d[b];
+    }
+    epnp::choose_control_points(c0, sc, n, cws);
+    epnp::control_inverse(cws, ci);
+    for (int i = 0; i < n; ++i) {
+        double a[4];
+        epnp::barycentric(ci, cws, pws + 3 * i, a);
+        const double du = cam.uc - us[2 * i], dv = cam.vc - us[2 * i + 1], q = du * du + dv * dv;
+        int k = 0;
+        for (int x = 0; x < 4; ++x)
+            for (int y = x; y < 4; ++y) {
+                const double aa = a[x] * a[y];
+                s[k] += aa; s[10 + k] += aa * du; s[20 + k] += aa * dv; s[30 + k] += aa * q;
+                ++k;
+            }
+        for (int j = 0; j < 4; ++j)
+            for (int c = 0; c < 3; ++c) s[40 + j * 3 + c] += a[j] * (pws[3 * i + c] - c0[c]);
+    }
+    double Rs[3][3][3], ts[3][3], err[3] = {0, 0, 0};
+    epnp::refit_candidates(s, n, c0, cws, ci, cam, pws, Rs, ts);
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) err[c] += epnp::reproj_dist(Rs[c], ts[c], pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
+    int N = 0;
+    if (err[1] < err[0]) N = 1;
+    if (err[2] < err[N]) N = 2;
+    epnp::rodrigues_to_vec(Rs[N], rvec);
+    for (int i = 0; i < 3; ++i) t3[i] = ts[N][i];
+}
 }
 
 // ---- CPU emulation of csrc/pnp_ransac.cu built from the same __host__ __device__ functions

@@ -99,7 +99,7 @@ def test_sentinel_returns(rec, frame):
 def test_planted_pose_end_to_end(rec, frame, seed, roi, rv, t):
     """Planted XYZ maps (ellipsoid under a known pose, 10 % outliers) replace the network outputs on both
     sides.  All byte/integer stages must agree bit for bit, the same candidate must win, and the final R|t must equal the
-    oracle's (real cv2.solvePnPRansac) to 1e-6 deg / 1e-9 relative (SURVEY section 8c allows 0.1 deg / 1e-3); both sit
+    oracle's (real cv2.solvePnPRansac) to 1e-5 deg / 1e-9 relative (SURVEY section 8c allows 0.1 deg / 1e-3); both sit
     within 2.5 deg / 3 % of the planted truth (uint8 XYZ quantisation, 10 % outliers, clipped crops)."""
     from oracle.recognition_oracle import Pix2PoseOracle
     R, t = rodrigues(rv), np.array(t)
@@ -113,7 +113,7 @@ def test_planted_pose_end_to_end(rec, frame, seed, roi, rv, t):
         xyz, mask, _ = _cand_crop(rec, c["cid"], c["box"])
         assert np.array_equal(xyz, c["xyz_u8"]) and np.array_equal(mask, np.asarray(c["valid_mask"], bool))
     ang = np.degrees(np.arccos(np.clip((np.trace(want[2].T @ got[2]) - 1) / 2, -1, 1)))
-    assert ang <= 1e-6 and np.linalg.norm(got[3] - want[3]) / np.linalg.norm(want[3]) <= 1e-9
+    assert ang <= 1e-5 and np.linalg.norm(got[3] - want[3]) / np.linalg.norm(want[3]) <= 1e-9
     assert got[4] == want[4]
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     ang_true = np.degrees(np.arccos(np.clip((np.trace(R.T @ got[2]) - 1) / 2, -1, 1)))

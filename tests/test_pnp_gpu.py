@@ -4,7 +4,7 @@ Tolerance, stated up front (SURVEY.md section 8c asks for <= 0.1 deg, ||dt||/||t
 OpenCV's RNG, subset draw, 5-point EPnP (incl. its own Jacobi SVD, bit for bit -- csrc/epnp_core.cuh), float32 scoring,
 acceptance rule, adaptive termination and the EPnP refit are replicated, so the bar here is much tighter than the
 survey's: the inlier INDEX SETS must be identical to cv2's in every trial (index work: bit-exact), and R|t of the refit on
-those inliers must agree to 1e-6 deg / 1e-9 relative (block-parallel sums instead of OpenCV's sequential ones; refits on
+those inliers must agree to 1e-5 deg / 1e-9 relative (block-parallel sums instead of OpenCV's sequential ones; refits on
 <= 32 inliers run OpenCV's exact operation order and must agree to 1e-12)."""
 import cv2
 import numpy as np
@@ -54,7 +54,7 @@ def test_matches_cv2_on_planted_poses():
         if len(inl) <= 32:
             assert np.abs(g_rv - rv).max() <= 1e-12 and dt <= 1e-12, (trial, n, len(inl), np.abs(g_rv - rv).max(), dt)
         else:
-            assert ang <= 1e-6 and dt <= 1e-9, (trial, n, of, ang, dt)
+            assert ang <= 1e-5 and np.abs(Rcv - g_R).max() <= 1e-10 and dt <= 1e-9, (trial, n, of, ang, dt)   # (acos resolves ~1e-6 deg)
         assert np.allclose(cv2.Rodrigues(g_rv)[0], g_R, atol=1e-12)     # R = Rodrigues(rvec), recognition.py:223
     assert total >= 40
 

@@ -54,7 +54,7 @@ def test_oracle_pnp_ransac_equals_reference():
 
 @pytest.mark.gpu
 def test_gpu_pnp_ransac_against_reference_vectors():
-    """Valid mask and inlier count exact (index work); R|t of the reference's cv2 call within 1e-6 deg / 1e-9 relative
+    """Valid mask and inlier count exact (index work); R|t of the reference's cv2 call within 1e-5 deg / 1e-9 relative
     (far inside SURVEY section 8c's 0.1 deg / 1e-3 / 1 %): OpenCV's EPnP-RANSAC is replicated hypothesis for hypothesis."""
     from pix2pose_b200 import weights as W
     from pix2pose_b200.recognition import pix2pose
@@ -66,7 +66,7 @@ def test_gpu_pnp_ransac_against_reference_vectors():
         Rw, tw, nw = G["pnp%d_R" % i], G["pnp%d_t" % i], int(G["pnp%d_ninl" % i])
         ang = np.degrees(np.arccos(np.clip((np.trace(Rw.T @ R) - 1) / 2, -1, 1)))
         assert np.array_equal(np.asarray(mask), G["pnp%d_mask" % i])            # valid mask: integer work, exact
-        assert n == nw and ang <= 1e-6 and np.linalg.norm(t - tw) / np.linalg.norm(tw) <= 1e-9, (i, ang, n, nw)
+        assert n == nw and ang <= 1e-5 and np.linalg.norm(t - tw) / np.linalg.norm(tw) <= 1e-9, (i, ang, n, nw)
     R, t, mask, n = rec.pnp_ransac(np.zeros((480, 640, 3), np.uint8), np.ones((20, 20)), np.zeros((20, 20), bool), 100, 120, 100, 120)
     assert n == -1 and np.array_equal(R, np.eye(3))
 
@@ -110,7 +110,7 @@ def test_oracle_est_pose_equals_reference_est_pose(cid):
 def test_gpu_est_pose_against_reference_est_pose(cid):
     """The product through the drop-in class with the same planted network outputs: bbox_t, the sentinel decision, the
     returned uint8 XYZ crop, the full-frame mask and the inlier fraction are integer work and must equal the reference's
-    exactly; R|t within 1e-6 deg / 1e-9 relative of the reference's result (SURVEY section 8c allows 0.1 deg / 1e-3)."""
+    exactly; R|t within 1e-5 deg / 1e-9 relative of the reference's result (SURVEY section 8c allows 0.1 deg / 1e-3)."""
     from pix2pose_b200 import weights as W
     from pix2pose_b200.recognition import pix2pose
     rec = pix2pose(W.synthetic_weights("resnet50", 1), K_LM, 640, 480, OBJ, backbone="resnet50", capacity=16, max_dets=16, **TH)
@@ -128,4 +128,4 @@ def test_gpu_est_pose_against_reference_est_pose(cid):
     assert np.array_equal(got[0], E["c%d_img_pred" % cid])          # same candidate wins: its uint8 crop comes back
     assert np.array_equal(np.packbits(got[1]), E["c%d_mask" % cid])
     assert got[4] == float(E["c%d_frac" % cid])                     # max_inlier / n_init_mask: integer ratio
-    assert ang <= 1e-6 and np.linalg.norm(got[3] - tw) / np.linalg.norm(tw) <= 1e-9, (ang, got[3], tw)
+    assert ang <= 1e-5 and np.linalg.norm(got[3] - tw) / np.linalg.norm(tw) <= 1e-9, (ang, got[3], tw)
