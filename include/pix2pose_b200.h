@@ -93,7 +93,10 @@ typedef struct p2p_det {
     double fu, fv, uc, vc; /* self.camK                                                             */
     double scale[3], ct[3]; /* obj_param                                                            */
     long long pool_off;  /* internal */
-    int cap_px, pad;     /* internal */
+    int cap_px, seg;     /* internal */
+    double th_o[8];      /* self.th_o (recognition.py:15) of this detection's object, first n_thresholds entries; read by
+                          * p2p_pipeline_run_multi only -- the single-object calls take them as arguments           */
+    double th_i;         /* self.th_i (recognition.py:16), likewise                                                  */
 } p2p_det_t;
 
 typedef struct p2p_pose {
@@ -116,10 +119,24 @@ P2P_API void p2p_pipeline_destroy(p2p_pipeline_t* p);
 P2P_API int p2p_pipeline_run(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames, int F, int H, int W,
                      const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
                      int iters, double confidence, p2p_pose_t* out);
+/* Same for a float32 image batch (F,H,W,3): tools/5_evaluation_bop_icp3d.py:369 hands est_pose a float32 copy of the
+ * frame whose invalid-depth pixels were scaled by 0.1 (non-integer values; numpy evaluates recognition.py:76-77, :114-115
+ * in float64 on them).  Crops are cut from the float values, nothing is truncated to uint8. */
+P2P_API int p2p_pipeline_run_f32(p2p_pipeline_t* p, const p2p_model_t* m, const float* frames, int F, int H, int W,
+                     const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                     int iters, double confidence, p2p_pose_t* out);
 /* Same with frames already on the device. */
 P2P_API int p2p_pipeline_run_device(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* frames_dev, int F, int H, int W,
                             const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
                             int iters, double confidence, p2p_pose_t* out);
+/* Detections of SEVERAL objects in one device run -- the per-object dispatch of tools/5_evaluation_bop_basic.py:289-304
+ * (`obj_pix2pose[model_ids_list.index(obj_id)].est_pose(image, roi)` per ROI, one resident model per object, :206-225):
+ * dets[] holds n_seg contiguous groups of seg_counts[s] detections, group s is evaluated with models[s]; obj_param,
+ * camK and the thresholds travel in each p2p_det_t.  frames_dev: device pointer from p2p_pipeline_upload_frames
+ * (uint8) -- or float32 frames when frames_f32 != 0. */
+P2P_API int p2p_pipeline_run_multi(p2p_pipeline_t* p, const p2p_model_t* const* models, const int* seg_counts, int n_seg,
+                           const void* frames_dev, int frames_f32, int F, int H, int W, const p2p_det_t* dets, int n,
+                           float reproj_err, int iters, double confidence, p2p_pose_t* out);
 /* After a run: winner's uint8 XYZ crop (h,w,3) and valid mask (h,w), h = best_box[5]-best_box[4], w = [7]-[6]. */
 P2P_API int p2p_pipeline_fetch_crop(p2p_pipeline_t* p, int det, const p2p_pose_t* rec, uint8_t* xyz, uint8_t* mask);
 /* After a run: mask-IoU ingredients of tools/5_evaluation_bop_basic.py:307-316 on the device.  masks: (n,H,W) uint8 detector
@@ -146,10 +163,19 @@ P2P_API int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float*
  * launched on). slot in [0,8). p2p_engine_event_elapsed synchronises on slot_b. */
 P2P_API int p2p_engine_event_record(p2p_engine_t* e, int slot);
 P2P_API int p2p_engine_event_elapsed(p2p_engine_t* e, int slot_a, int slot_b, float* ms);
+/* Measurement across whole pipeline runs: between _begin and _end every generator launch of this engine is bracketed by
+ * CUDA events on its stream (runs are then issued kernel by kernel instead of as a captured graph); _end returns the
+ * summed milliseconds of the tcgen05 convolution launches (ms[0]) and of the other generator kernels (ms[1]) and their
+ * launch counts.  bench.py derives roofline.achieved from it on the real step, not on an isolated forward. */
+P2P_API int p2p_engine_prof_begin(p2p_engine_t* e);
+P2P_API int p2p_engine_prof_end(p2p_engine_t* e, double* ms, int* counts);
 /* Measurement: one forward of n <= capacity crops with every launch bracketed by CUDA events;
  * ms[0] = summed duration of the tcgen05 conv launches, ms[1] = other kernels, counts[0..1] likewise. */
 P2P_API int p2p_engine_profile_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, double* ms, int* counts);
-/* Copies frames to a pipeline-owned device buffer (for p2p_pipeline_run_device); *dev receives the pointer. */
+/* Copies frames to one of two rotating pipeline-owned device buffers (for p2p_pipeline_run_device / _run_multi); *dev
+ * receives the pointer.  The copy is issued on a copy stream and the call returns at once: the frames of the next batch
+ * travel while the previous batch computes, and the run that consumes *dev waits for the copy on the device.  With pinned
+ * host memory (p2p_host_alloc) the caller must leave `frames` untouched until that run has returned. */
 P2P_API int p2p_pipeline_upload_frames(p2p_pipeline_t* p, const uint8_t* frames, int F, int H, int W, void** dev);
 /* Page-locked host buffers for the end-to-end path (bench.py `e2e`). */
 P2P_API void* p2p_host_alloc(size_t bytes);

@@ -62,6 +62,10 @@ def lib():
         "p2p_pipeline_destroy": (None, [vp]),
         "p2p_pipeline_run": (ctypes.c_int, [vp, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                             ctypes.c_int, c_d, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
+        "p2p_pipeline_run_f32": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                                ctypes.c_int, c_d, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
+        "p2p_pipeline_run_multi": (ctypes.c_int, [vp, ctypes.POINTER(vp), c_i, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
         "p2p_pipeline_run_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                                    ctypes.c_int, c_d, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_double, vp]),
         "p2p_pipeline_fetch_crop": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8)]),
@@ -80,6 +84,8 @@ def lib():
         "p2p_time_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]),
         "p2p_engine_event_record": (ctypes.c_int, [vp, ctypes.c_int]),
         "p2p_engine_event_elapsed": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_f]),
+        "p2p_engine_prof_begin": (ctypes.c_int, [vp]),
+        "p2p_engine_prof_end": (ctypes.c_int, [vp, c_d, c_i]),
         "p2p_engine_profile_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, c_d, c_i]),
         "p2p_pipeline_upload_frames": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                       ctypes.POINTER(vp)]),

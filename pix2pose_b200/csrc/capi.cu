@@ -120,7 +120,23 @@ int p2p_pipeline_run_device(p2p_pipeline_t* p, const p2p_model_t* m, const uint8
                             int iters, double confidence, p2p_pose_t* out) {
     return guarded([&] {
         P2P_CHECK(p && m, "NULL argument");
-        p->p->run(*m->m, frames_dev, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
+        P2P_CHECK(th_outlier, "NULL argument");
+        const Model* mm = m->m.get();
+        p->p->run(&mm, &n, 1, frames_dev, false, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err,
+                  iters, confidence, reinterpret_cast<PoseRecord*>(out));
+    });
+}
+
+int p2p_pipeline_run_f32(p2p_pipeline_t* p, const p2p_model_t* m, const float* frames, int F, int H, int W,
+                         const p2p_det_t* dets, int n, const double* th_outlier, double th_inlier, float reproj_err,
+                         int iters, double confidence, p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p && m && frames, "NULL argument");
+        P2P_CHECK(F >= 1 && H >= 1 && W >= 1, "bad frame batch shape");
+        P2P_CHECK(th_outlier, "NULL argument");
+        const void* fd = p->p->upload_frames(frames, true, F, H, W);
+        const Model* mm = m->m.get();
+        p->p->run(&mm, &n, 1, fd, true, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
                   confidence, reinterpret_cast<PoseRecord*>(out));
     });
 }
@@ -131,9 +147,26 @@ int p2p_pipeline_run(p2p_pipeline_t* p, const p2p_model_t* m, const uint8_t* fra
     return guarded([&] {
         P2P_CHECK(p && m && frames, "NULL argument");
         P2P_CHECK(F >= 1 && H >= 1 && W >= 1, "bad frame batch shape");
-        const uint8_t* fd = p->p->upload_frames(frames, F, H, W);
-        p->p->run(*m->m, fd, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
+        P2P_CHECK(th_outlier, "NULL argument");
+        const void* fd = p->p->upload_frames(frames, false, F, H, W);
+        const Model* mm = m->m.get();
+        p->p->run(&mm, &n, 1, fd, false, F, H, W, reinterpret_cast<const DetIn*>(dets), n, th_outlier, th_inlier, reproj_err, iters,
                   confidence, reinterpret_cast<PoseRecord*>(out));
+    });
+}
+
+int p2p_pipeline_run_multi(p2p_pipeline_t* p, const p2p_model_t* const* models, const int* seg_counts, int n_seg,
+                           const void* frames_dev, int frames_f32, int F, int H, int W, const p2p_det_t* dets, int n,
+                           float reproj_err, int iters, double confidence, p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p && models && seg_counts && n_seg >= 1 && n_seg <= 4096, "bad argument");
+        std::vector<const Model*> mm(n_seg);
+        for (int i = 0; i < n_seg; ++i) {
+            P2P_CHECK(models[i], "segment %d has no model", i);
+            mm[i] = models[i]->m.get();
+        }
+        p->p->run(mm.data(), seg_counts, n_seg, frames_dev, frames_f32 != 0, F, H, W, reinterpret_cast<const DetIn*>(dets), n, nullptr,
+                  0.0, reproj_err, iters, confidence, reinterpret_cast<PoseRecord*>(out));
     });
 }
 
@@ -244,11 +277,27 @@ int p2p_engine_profile_forward(p2p_engine_t* e, const p2p_model_t* m, const floa
         counts[0] = static_cast<int>(prof[2]); counts[1] = static_cast<int>(prof[3]);
     });
 }
+int p2p_engine_prof_begin(p2p_engine_t* e) {
+    return guarded([&] {
+        P2P_CHECK(e, "NULL argument");
+        Engine& E = *e->e;
+        for (double& v : E.prof_acc) v = 0;
+        E.prof = E.prof_acc;
+    });
+}
+int p2p_engine_prof_end(p2p_engine_t* e, double* ms, int* counts) {
+    return guarded([&] {
+        P2P_CHECK(e && ms && counts, "NULL argument");
+        Engine& E = *e->e;
+        E.prof = nullptr;
+        ms[0] = E.prof_acc[0]; ms[1] = E.prof_acc[1];
+        counts[0] = static_cast<int>(E.prof_acc[2]); counts[1] = static_cast<int>(E.prof_acc[3]);
+    });
+}
 int p2p_pipeline_upload_frames(p2p_pipeline_t* p, const uint8_t* frames, int F, int H, int W, void** dev) {
     return guarded([&] {
         P2P_CHECK(p && frames && dev, "NULL argument");
-        *dev = const_cast<uint8_t*>(p->p->upload_frames(frames, F, H, W));
-        P2P_CUDA(cudaStreamSynchronize(p->p->engine->stream));
+        *dev = const_cast<void*>(p->p->upload_frames(frames, false, F, H, W));   // asynchronous (copy stream); the run waits for it
     });
 }
 

@@ -123,6 +123,7 @@ class Engine {
     // Measurement: when `prof` is set, forward() brackets every launch with CUDA events on its stream and
     // adds the elapsed times (ms) to prof[0] (tcgen05 conv kernels) / prof[1] (other kernels); counts in prof[2..3].
     double* prof = nullptr;
+    double prof_acc[4] = {0, 0, 0, 0};   // target of p2p_engine_prof_begin / _end (profiling across whole pipeline runs)
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // user timing slots
 };
 

@@ -189,7 +189,7 @@ P2P_HD inline double cv_hypot(double a, double b) {   // lapack.cpp's local hypo
 // On the device every instance (3x3, 6x3, 6x4, 6x5) is fully unrolled over rows, pairs and columns (only the sweep loop
 // stays a loop; the descending selection sort swaps under a predicate instead of through a computed row index), so
 // At / Vt / W are only ever indexed statically and live in registers rather than in local memory.
-#if defined(__CUDACC__)
+#if defined(__CUDA_ARCH__)
 #define P2P_UNROLL _Pragma("unroll")
 #else
 #define P2P_UNROLL
@@ -340,15 +340,15 @@ P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
         bool changed = false;
         for (int i = 0; i < N - 1; ++i) {
             double ri[N];
-#pragma unroll
+P2P_UNROLL
             for (int k = 0; k < N; ++k) ri[k] = P2P_AT(i, k);
             bool dirty = false;
             for (int j = i + 1; j < N; ++j) {
                 double rj[N];
-#pragma unroll
+P2P_UNROLL
                 for (int k = 0; k < N; ++k) rj[k] = P2P_AT(j, k);
                 double a = 0, b = 0, p = 0;
-#pragma unroll
+P2P_UNROLL
                 for (int k = 0; k < N; ++k) {
                     a += ri[k] * ri[k];
                     b += rj[k] * rj[k];
@@ -366,7 +366,7 @@ P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
                     c = sqrt((gamma + beta) / (gamma * 2));
                     s = p / (gamma * c * 2);
                 }
-#pragma unroll
+P2P_UNROLL
                 for (int k = 0; k < N; ++k) {
                     const double x = ri[k], y = rj[k];
                     ri[k] = c * x + s * y;
@@ -375,7 +375,7 @@ P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
                 dirty = true;
             }
             if (dirty) {
-#pragma unroll
+P2P_UNROLL
                 for (int k = 0; k < N; ++k) P2P_AT(i, k) = ri[k];
                 changed = true;
             }
@@ -384,7 +384,7 @@ P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
     }
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-#pragma unroll
+P2P_UNROLL
         for (int k = 0; k < N; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
         W[i] = sqrt(sd);
     }
@@ -424,7 +424,7 @@ P2P_HD inline void cv_jacobi_svd12_ut(double* At, double* W) {
             sd = sqrt(sd);
         }
         const double sc = sd > minval ? 1 / sd : 0.;
-#pragma unroll
+P2P_UNROLL
         for (int k = 0; k < N; ++k) P2P_AT(i, k) *= sc;
     }
 #undef P2P_AT

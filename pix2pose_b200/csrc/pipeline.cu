@@ -74,8 +74,10 @@ __device__ __forceinline__ bool box_too_small(const int* b) {
 // ------------------------------------------------------------------------------------------------
 // P1 / P3: crop + normalise + zero-pad + bilinear resize to 128x128 ('reflect'); P3 also zeroes the
 // background given by the resized stage-1 mask (recognition.py:75-82, :103-121)
-template <bool STAGE2>
-__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frames, int H, int W,
+// PIX = uint8_t (the BOP drivers) or float (tools/5_evaluation_bop_icp3d.py:369 hands est_pose a float32 image whose
+// invalid-depth pixels were scaled by 0.1: non-integer values; numpy promotes `pixel - [128,128,128]` to float64 either way)
+template <bool STAGE2, typename PIX>
+__global__ void __launch_bounds__(256) crop_resize_kernel(const PIX* __restrict__ frames, int H, int W,
                                                           const DetIn* __restrict__ dets, const DetState* __restrict__ state,
                                                           const uint8_t* __restrict__ bits1, int n_th, float* __restrict__ x) {
     int d, k = 0;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
     const Lerp ly = axis_map(oy, side_v, 128), lx = axis_map(ox, side_u, 128);
     const int rr[2] = {reflect_idx(ly.lo, side_v), reflect_idx(ly.hi, side_v)};
     const int cc[2] = {reflect_idx(lx.lo, side_u), reflect_idx(lx.hi, side_u)};
-    const uint8_t* fr = frames + static_cast<long long>(det.frame) * H * W * 3;
+    const PIX* fr = frames + static_cast<long long>(det.frame) * H * W * 3;
     const int s1v = b1[1] - b1[0], s1u = b1[3] - b1[2];
     double pix[2][2][3];
 #pragma unroll
@@ -146,8 +148,7 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
 // P2: stage-1 masks, counts, bbox / centroid reductions, refined boxes (recognition.py:85-111)
 __global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restrict__ dets, DetState* __restrict__ state,
                                                           const float* __restrict__ dec1, const float* __restrict__ prob1,
-                                                          uint8_t* __restrict__ bits1, const double* __restrict__ th_o, int n_th,
-                                                          int H, int W, double box_size) {
+                                                          uint8_t* __restrict__ bits1, int n_th, int H, int W, double box_size) {
     __shared__ int s_cnt[kMaxTh], s_n, s_minv, s_maxv, s_minu, s_maxu;
     __shared__ long long s_sumv, s_sumu;
     const int d = blockIdx.x;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restric
         return;
     }
     float thf[kMaxTh];
-    for (int t = 0; t < n_th; ++t) thf[t] = static_cast<float>(th_o[t]);
+    for (int t = 0; t < n_th; ++t) thf[t] = static_cast<float>(det.th_o[t]);   // prob is float32: numpy compares in float32
     int cnt[kMaxTh] = {0, 0, 0, 0, 0, 0, 0, 0};
     int n = 0, minv = 1 << 30, maxv = -1, minu = 1 << 30, maxu = -1;
     long long sumv = 0, sumu = 0;
@@ -202,7 +203,9 @@ __global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restric
         const int cx_m = static_cast<int>((static_cast<double>(s_sumu) / s_n - (127 / 2.0)) + cx_o);     // :108
         const int cy_m = static_cast<int>((static_cast<double>(s_sumv) / s_n - (127 / 2.0)) + cy_o);     // :109
         int box2[12];
-        get_boxes_dev(box_size, bb, H, W, true, cy_m, cx_m, static_cast<double>(w_stage_1), box2);        // :110
+        // :110 -- get_boxes treats ct[0] == -1 as "no centre given" (:29) and falls back to the bbox centre, also for a
+        // computed centre row that happens to be -1 (ROIs at the top image edge)
+        get_boxes_dev(box_size, bb, H, W, cy_m != -1, cy_m, cx_m, static_cast<double>(w_stage_1), box2);
         for (int i = 0; i < 12; ++i) appended[n_app][i] = box2[i];                                        // :111
         ++n_app;
         if (box_too_small(box2)) continue;                                                                // :116-119
@@ -216,19 +219,24 @@ __global__ void __launch_bounds__(256) stage1_post_kernel(const DetIn* __restric
     st.n_cand = nc;
 }
 
-// compact candidate numbering over the batch + per-chunk live counts for the stage-2 forwards
-// One block of 256 threads: thread t owns detections t, t + 256, ...; block-wide exclusive scan of n_cand per round (a single
-// thread walking the 900-byte DetState records paid one global-load latency per detection: 144 us for 256 detections).
-__global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ state, CandStats* __restrict__ cands, int n_det,
-                                                        int* __restrict__ n_active, int n_chunks, int chunk) {
+// Compact candidate numbering within each model segment + live counts per stage-2 forward chunk.
+// One block of 256 threads per segment: thread t owns detections t, t + 256, ... of the segment; block-wide exclusive scan of
+// n_cand per round (a single thread walking the 900-byte DetState records paid one global-load latency per detection:
+// 144 us for 256 detections).  Candidates of segment s occupy slots seg_start[s] * n_th + 0 .. live_s - 1.
+__global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ state, CandStats* __restrict__ cands,
+                                                        const int* __restrict__ seg_tab, int n_seg, int n_th,
+                                                        int* __restrict__ n_active, int chunk) {
     __shared__ int s_w[8];
     __shared__ int s_carry;
+    const int seg = blockIdx.x;
+    const int d_begin = seg_tab[seg], d_end = seg_tab[seg + 1];
+    const int slot0 = d_begin * n_th;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int d0 = 0; d0 < n_det; d0 += 256) {
+    for (int d0 = d_begin; d0 < d_end; d0 += 256) {
         const int d = d0 + threadIdx.x;
-        const int nc = d < n_det ? state[d].n_cand : 0;
+        const int nc = d < d_end ? state[d].n_cand : 0;
         int incl = nc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -240,11 +248,11 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ s
         int base = s_carry;
         for (int w = 0; w < warp; ++w) base += s_w[w];
         base += incl - nc;
-        if (d < n_det) {
-            state[d].cand_base = base;
+        if (d < d_end) {
+            state[d].cand_base = slot0 + base;
             for (int k = 0; k < nc; ++k) {
-                cands[base + k].det = d;
-                cands[base + k].k = k;
+                cands[slot0 + base + k].det = d;
+                cands[slot0 + base + k].k = k;
             }
         }
         __syncthreads();
@@ -253,8 +261,8 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ s
     }
     if (threadIdx.x == 0) {
         const int total = s_carry;
-        for (int j = 0; j < n_chunks; ++j) n_active[j] = max(0, min(chunk, total - j * chunk));
-        n_active[n_chunks] = total;
+        const int c0 = seg_tab[n_seg + 1 + seg], c1 = seg_tab[n_seg + 1 + seg + 1];
+        for (int j = 0; j < c1 - c0; ++j) n_active[c0 + j] = max(0, min(chunk, total - j * chunk));
     }
 }
 
@@ -263,15 +271,13 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(DetState* __restrict__ s
 constexpr int kPostThreads = 512;
 
 __global__ void __launch_bounds__(kPostThreads, 2) stage2_post_kernel(const DetIn* __restrict__ dets, const DetState* __restrict__ state,
-                                                                   CandStats* __restrict__ cands, const int* __restrict__ n_total,
+                                                                   CandStats* __restrict__ cands,
                                                                    const float* __restrict__ dec2, const float* __restrict__ prob2,
-                                                                   int n_th, double th_i, uint8_t* __restrict__ xyz_u8,
+                                                                   int n_th, uint8_t* __restrict__ xyz_u8,
                                                                    uint8_t* __restrict__ valid, float* __restrict__ obj,
                                                                    float* __restrict__ img, PnpProblem* __restrict__ problems) {
     const int c = blockIdx.x;
-    if (c >= *n_total) {
-        return;
-    }
+    if (cands[c].det < 0) return;   // slot past its segment's live candidates
     __shared__ float s_pmin, s_pmax, s_imin, s_imax;
     __shared__ int s_ng128, s_base, s_nng;
     __shared__ long long s_sv, s_su;
@@ -279,6 +285,7 @@ __global__ void __launch_bounds__(kPostThreads, 2) stage2_post_kernel(const DetI
     const int d = cs.det, k = cs.k;
     const DetIn& det = dets[d];
     const int* b = state[d].pair_box[k];
+    const double th_i = det.th_i;
     const float* dc = dec2 + static_cast<long long>(c) * 16384 * 3;
     const float* pb = prob2 + static_cast<long long>(c) * 16384;
     if (threadIdx.x == 0) {
@@ -564,26 +571,115 @@ Pipeline::Pipeline(Engine* eng, int max_dets_, int n_th_) : engine(eng), max_det
     x1_.alloc(D * 16384 * 3); dec1_.alloc(D * 16384 * 3); prob1_.alloc(D * 16384);
     x2_.alloc(C * 16384 * 3); dec2_.alloc(C * 16384 * 3); prob2_.alloc(C * 16384);
     bits1_.alloc(D * 16384);
-    n_active_.alloc(C / std::max(1, eng->cap) + 3);
-    th_.alloc(kMaxTh);
     problems_.alloc(C); pnp_res_.alloc(C);
+    P2P_CUDA(cudaMallocHost(&pinned_dets_, sizeof(DetIn) * D));
+    P2P_CUDA(cudaMallocHost(&pinned_recs_, sizeof(PoseRecord) * D));
+    if (const char* e = getenv("P2P_GRAPH")) use_graph = atoi(e) != 0;
 }
-Pipeline::~Pipeline() {}
+Pipeline::~Pipeline() {
+    for (auto& g : graphs_)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    if (pinned_dets_) cudaFreeHost(pinned_dets_);
+    if (pinned_recs_) cudaFreeHost(pinned_recs_);
+    if (copy_stream_) {
+        cudaStreamDestroy(copy_stream_);
+        for (auto& e : frames_ready_) cudaEventDestroy(e);
+        for (auto& e : frames_free_) cudaEventDestroy(e);
+    }
+}
 
 void Pipeline::ensure_pool(long long px) {
     if (px <= pool_px_) return;
     pool_px_ = px + px / 4;
     xyz_u8_.alloc(pool_px_ * 3); valid_.alloc(pool_px_); pnp_mask_.alloc(pool_px_);
     obj_.alloc(pool_px_ * 3); img_.alloc(pool_px_ * 2);
+    ++pool_gen_;   // captured graphs hold the old pointers
 }
 
-void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, int W, const DetIn* dets, int n,
-                   const double* th_o, double th_i, float reproj_err, int iters, double confidence, PoseRecord* out) {
+// The kernels of one run, in stream order.  Nothing here depends on values the host does not already have: live counts
+// stay on the device (n_active_, CandStats::det), so the sequence can be captured into a CUDA graph.
+void Pipeline::enqueue(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H,
+                       int W, int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s) {
+    const int cap = engine->cap;
+    const int C = n * n_th;
+    const uint8_t* fr_u8 = static_cast<const uint8_t*>(frames_dev);
+    const float* fr_f32 = static_cast<const float*>(frames_dev);
+    // stage 1
+    if (frames_f32) crop_resize_kernel<false, float><<<dim3(n, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
+    else crop_resize_kernel<false, uint8_t><<<dim3(n, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
+    P2P_CUDA(cudaGetLastError());
+    for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg)
+        for (int b = 0; b < seg_counts[sg]; b += cap) {
+            const int nb = std::min(cap, seg_counts[sg] - b);
+            const size_t at = static_cast<size_t>(d0 + b);
+            engine->forward(*models[sg], x1_.p + at * 16384 * 3, nb, dec1_.p + at * 16384 * 3, prob1_.p + at * 16384, nullptr, s);
+        }
+    if (!ov_dec_[0].empty()) {   // parity hook (never inside a captured graph)
+        P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaStreamSynchronize(s));
+        ov_dec_[0].clear(); ov_prob_[0].clear();
+    }
+    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, n_th, H, W, box_size);
+    P2P_CUDA(cudaGetLastError());
+    P2P_CUDA(cudaMemsetAsync(cands_.p, 0xff, sizeof(CandStats) * C, s));    // det = -1: slot not (yet) a live candidate
+    cand_scan_kernel<<<n_seg, 256, 0, s>>>(state_.p, cands_.p, seg_tab_.p, n_seg, n_th, n_active_.p, cap);
+    P2P_CUDA(cudaGetLastError());
+    // stage 2
+    if (frames_f32) crop_resize_kernel<true, float><<<dim3(C, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
+    else crop_resize_kernel<true, uint8_t><<<dim3(C, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
+    P2P_CUDA(cudaGetLastError());
+    for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg) {
+        const int Cs = seg_counts[sg] * n_th;
+        const int c0 = host_seg_[n_seg + 1 + sg];
+        for (int j = 0; j * cap < Cs; ++j) {
+            const int nb = std::min(cap, Cs - j * cap);
+            const size_t at = static_cast<size_t>(d0) * n_th + static_cast<size_t>(j) * cap;
+            engine->forward(*models[sg], x2_.p + at * 16384 * 3, nb, dec2_.p + at * 16384 * 3, prob2_.p + at * 16384,
+                            n_active_.p + c0 + j, s);
+        }
+    }
+    if (!ov_dec_[1].empty()) {
+        P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+        P2P_CUDA(cudaStreamSynchronize(s));
+        ov_dec_[1].clear(); ov_prob_[1].clear();
+    }
+    P2P_CUDA(cudaMemsetAsync(problems_.p, 0, sizeof(PnpProblem) * C, s));  // dead slots: n = 0 -> skipped by the PnP kernels
+    stage2_post_kernel<<<C, kPostThreads, 0, s>>>(dets_.p, state_.p, cands_.p, dec2_.p, prob2_.p, n_th, xyz_u8_.p, valid_.p, obj_.p,
+                                                  img_.p, problems_.p);
+    P2P_CUDA(cudaGetLastError());
+    launches += 5;
+    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s, max_cap);
+    select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
+    P2P_CUDA(cudaGetLastError());
+    launches += 1;
+}
+
+void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int F, int H,
+                   int W, const DetIn* dets, int n, const double* th_o, double th_i, float reproj_err, int iters, double confidence,
+                   PoseRecord* out) {
     P2P_CHECK(n >= 0 && n <= max_dets, "run: %d detections, pipeline built for %d", n, max_dets);
     if (n == 0) return;
-    P2P_CHECK(frames_dev && dets && th_o && out, "NULL argument");
+    P2P_CHECK(frames_dev && dets && out && models && seg_counts && n_seg >= 1, "NULL argument");
     cudaStream_t s = engine->stream;
     host_dets_.assign(dets, dets + n);
+    host_seg_.assign(2 * (n_seg + 1), 0);
+    {
+        int tot = 0, chunks = 0;
+        for (int sg = 0; sg < n_seg; ++sg) {
+            P2P_CHECK(models[sg] && seg_counts[sg] >= 1, "segment %d: empty or without a model", sg);
+            host_seg_[sg] = tot;
+            host_seg_[n_seg + 1 + sg] = chunks;
+            for (int d = tot; d < tot + seg_counts[sg] && d < n; ++d) host_dets_[d].seg = sg;
+            tot += seg_counts[sg];
+            chunks += (seg_counts[sg] * n_th + engine->cap - 1) / engine->cap;
+        }
+        P2P_CHECK(tot == n, "segment counts sum to %d, %d detections given", tot, n);
+        host_seg_[n_seg] = tot;
+        host_seg_[2 * n_seg + 1] = chunks;
+        if (n_active_.n < static_cast<size_t>(chunks + 1)) n_active_.alloc(chunks + 1);
+    }
     long long px = 0;
     int max_cap = 0;
     for (int d = 0; d < n; ++d) {
@@ -594,59 +690,67 @@ void Pipeline::run(const Model& model, const uint8_t* frames_dev, int F, int H, 
         di.pool_off = px;
         max_cap = std::max(max_cap, di.cap_px);
         px += static_cast<long long>(di.cap_px) * n_th;
+        if (th_o) {
+            for (int t = 0; t < kMaxTh; ++t) di.th_o[t] = t < n_th ? th_o[t] : 0.0;
+            di.th_i = th_i;
+        }
     }
     ensure_pool(px + 1);
-    dets_.upload(host_dets_.data(), n, s);
-    double th[kMaxTh] = {0};
-    for (int t = 0; t < n_th; ++t) th[t] = th_o[t];
-    th_.upload(th, kMaxTh, s);
-    const int cap = engine->cap;
+    pnp.reserve(n * n_th, iters);
+    int fslot = -1;
+    for (int i = 0; i < 2; ++i)
+        if (frames_[i].p && frames_dev == frames_[i].p) fslot = i;
+    if (fslot >= 0) P2P_CUDA(cudaStreamWaitEvent(s, frames_ready_[fslot], 0));
+    memcpy(pinned_dets_, host_dets_.data(), sizeof(DetIn) * n);
+    P2P_CUDA(cudaMemcpyAsync(dets_.p, pinned_dets_, sizeof(DetIn) * n, cudaMemcpyHostToDevice, s));
+    seg_tab_.upload(host_seg_.data(), host_seg_.size(), s);
 
-    // stage 1
-    crop_resize_kernel<false><<<dim3(n, 64), 256, 0, s>>>(frames_dev, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
-    P2P_CUDA(cudaGetLastError());
-    for (int b = 0; b < n; b += cap) {
-        const int nb = std::min(cap, n - b);
-        engine->forward(model, x1_.p + static_cast<size_t>(b) * 16384 * 3, nb, dec1_.p + static_cast<size_t>(b) * 16384 * 3,
-                        prob1_.p + static_cast<size_t>(b) * 16384, nullptr, s);
+    const bool overrides = !ov_dec_[0].empty() || !ov_dec_[1].empty();
+    static const bool prof_pnp = getenv("P2P_PROF_PNP") && atoi(getenv("P2P_PROF_PNP")) != 0;
+    if (use_graph && !overrides && !prof_pnp && !engine->prof) {
+        // everything a kernel argument or a grid dimension depends on
+        std::vector<long long> key = {n, n_seg, H, W, frames_f32 ? 1 : 0, reinterpret_cast<long long>(frames_dev), iters,
+                                      static_cast<long long>(reproj_err * 4096.0), static_cast<long long>(confidence * 1e9),
+                                      static_cast<long long>(box_size * 1e6), pool_gen_, (max_cap + 2047) / 2048};
+        for (int sg = 0; sg < n_seg; ++sg) {
+            key.push_back(reinterpret_cast<long long>(models[sg]));
+            key.push_back(seg_counts[sg]);
+        }
+        auto it = graphs_.find(key);
+        if (it == graphs_.end()) {
+            if (graphs_.size() >= 32) {   // bounded cache: drop everything rather than track recency
+                for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+                graphs_.clear();
+            }
+            const long long l0 = launches + pnp.launches + engine->launches;
+            cudaGraph_t graph = nullptr;
+            P2P_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            try {
+                enqueue(models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
+            } catch (...) {
+                cudaStreamEndCapture(s, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            P2P_CUDA(cudaStreamEndCapture(s, &graph));
+            GraphEntry ge;
+            ge.launches = launches + pnp.launches + engine->launches - l0;
+            cudaError_t err = cudaGraphInstantiate(&ge.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            P2P_CUDA(err);
+            it = graphs_.emplace(key, ge).first;
+        } else {
+            launches += it->second.launches;   // the counters only saw these kernels while they were captured
+        }
+        P2P_CUDA(cudaGraphLaunch(it->second.exec, s));
+    } else {
+        // debug / profiling path: kernel by kernel, with the parity hooks that replace the network outputs
+        enqueue(models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
     }
-    if (!ov_dec_[0].empty()) {
-        P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaStreamSynchronize(s));
-        ov_dec_[0].clear(); ov_prob_[0].clear();
-    }
-    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, th_.p, n_th, H, W, box_size);
-    P2P_CUDA(cudaGetLastError());
-    const int C = n * n_th;
-    const int n_chunks = (C + cap - 1) / cap;
-    cand_scan_kernel<<<1, 256, 0, s>>>(state_.p, cands_.p, n, n_active_.p, n_chunks, cap);
-    P2P_CUDA(cudaGetLastError());
-    // stage 2
-    crop_resize_kernel<true><<<dim3(C, 64), 256, 0, s>>>(frames_dev, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
-    P2P_CUDA(cudaGetLastError());
-    for (int j = 0; j < n_chunks; ++j) {
-        const int nb = std::min(cap, C - j * cap);
-        engine->forward(model, x2_.p + static_cast<size_t>(j) * cap * 16384 * 3, nb, dec2_.p + static_cast<size_t>(j) * cap * 16384 * 3,
-                        prob2_.p + static_cast<size_t>(j) * cap * 16384, n_active_.p + j, s);
-    }
-    if (!ov_dec_[1].empty()) {
-        P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaStreamSynchronize(s));
-        ov_dec_[1].clear(); ov_prob_[1].clear();
-    }
-    P2P_CUDA(cudaMemsetAsync(problems_.p, 0, sizeof(PnpProblem) * C, s));  // slots past the live count: n = 0 -> skipped
-    stage2_post_kernel<<<C, kPostThreads, 0, s>>>(dets_.p, state_.p, cands_.p, n_active_.p + n_chunks, dec2_.p, prob2_.p, n_th, th_i,
-                                                  xyz_u8_.p, valid_.p, obj_.p, img_.p, problems_.p);
-    P2P_CUDA(cudaGetLastError());
-    launches += 5;
-    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s, max_cap);
-    select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
-    P2P_CUDA(cudaGetLastError());
-    launches += 1;
-    P2P_CUDA(cudaMemcpyAsync(out, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
+    if (fslot >= 0) P2P_CUDA(cudaEventRecord(frames_free_[fslot], s));
+    P2P_CUDA(cudaMemcpyAsync(pinned_recs_, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
     P2P_CUDA(cudaStreamSynchronize(s));
+    memcpy(out, pinned_recs_, sizeof(PoseRecord) * n);
 }
 
 void Pipeline::fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out) {
@@ -697,11 +801,26 @@ void Pipeline::set_override(int stage, const float* dec, const float* prob, int 
     ov_prob_[stage - 1].assign(prob, prob + static_cast<size_t>(n) * 16384);
 }
 
-const uint8_t* Pipeline::upload_frames(const uint8_t* frames_host, int F, int H, int W) {
-    const size_t bytes = static_cast<size_t>(F) * H * W * 3;
-    if (frames_.n < bytes) frames_.alloc(bytes);
-    P2P_CUDA(cudaMemcpyAsync(frames_.p, frames_host, bytes, cudaMemcpyHostToDevice, engine->stream));
-    return frames_.p;
+const void* Pipeline::upload_frames(const void* frames_host, bool f32, int F, int H, int W) {
+    // Two rotating device buffers filled on a copy stream: the frames of the next batch can travel while the previous
+    // batch is still computing; run() makes the compute stream wait for the copy it consumes.
+    const size_t bytes = static_cast<size_t>(F) * H * W * 3 * (f32 ? sizeof(float) : 1);
+    if (!copy_stream_) {
+        P2P_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        for (auto& e : frames_ready_) P2P_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : frames_free_) P2P_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int slot = frames_next_;
+    frames_next_ ^= 1;
+    if (frames_[slot].n < bytes) {
+        P2P_CUDA(cudaStreamSynchronize(engine->stream));   // a run may still be reading the old allocation
+        frames_[slot].alloc(bytes);
+        ++pool_gen_;
+    }
+    P2P_CUDA(cudaStreamWaitEvent(copy_stream_, frames_free_[slot], 0));   // last run that read this buffer has finished
+    P2P_CUDA(cudaMemcpyAsync(frames_[slot].p, frames_host, bytes, cudaMemcpyHostToDevice, copy_stream_));
+    P2P_CUDA(cudaEventRecord(frames_ready_[slot], copy_stream_));
+    return frames_[slot].p;
 }
 
 }  // namespace p2p

@@ -7,6 +7,9 @@
 #pragma once
 #include <stdint.h>
 
+#include <map>
+#include <vector>
+
 #include "common.cuh"
 #include "engine.cuh"
 #include "pnp_ransac.cuh"
@@ -25,7 +28,9 @@ struct DetIn {
     double scale[3], ct[3];     // obj_param (recognition.py:17-18)
     long long pool_off;         // first pixel slot of this detection's candidate pools
     int cap_px;                 // pixels reserved per candidate (side1^2)
-    int pad;
+    int seg;                    // index of the model (object) segment this detection belongs to (internal)
+    double th_o[kMaxTh];        // self.th_o of the detection's object (cfg_tless_paper.json gives every object its own)
+    double th_i;                // self.th_i
 };
 
 // Stage-1 statistics and the stage-2 candidates of one detection (device-written).
@@ -68,10 +73,14 @@ class Pipeline {
   public:
     Pipeline(Engine* engine, int max_dets, int n_th);
     ~Pipeline();
-    // frames_dev: (F,H,W,3) uint8 on the device; dets: host array of n (<= max_dets).
+    // frames_dev: (F,H,W,3) uint8 (or float32 when frames_f32) on the device; dets: host array of n (<= max_dets).
     // Results are copied to `out` (host).  th_o has n_th entries.
-    void run(const Model& model, const uint8_t* frames_dev, int F, int H, int W, const DetIn* dets, int n,
-             const double* th_o, double th_i, float reproj_err, int iters, double confidence, PoseRecord* out);
+    // Detections of several objects in one run: `dets` holds n_seg contiguous segments of seg_counts[s] detections, segment s
+    // is evaluated with models[s] (only the generator forwards are per segment; crops, post-processing, PnP and selection
+    // run over the whole batch).  th_o == nullptr: thresholds are taken from each DetIn; otherwise th_o / th_i apply to all.
+    void run(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int F, int H,
+             int W, const DetIn* dets, int n, const double* th_o, double th_i, float reproj_err, int iters, double confidence,
+             PoseRecord* out);
     // After run(): copy the winner's uint8 XYZ crop (h,w,3) and valid mask (h,w) of detection d
     // (h = v2-v1, w = u2-u1 of best_box) into host buffers sized for cap_px pixels.
     void fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out);
@@ -85,8 +94,8 @@ class Pipeline {
     // Test hook: replace the network outputs of `stage` (1|2) in the NEXT run by these host arrays
     // (n crops of decode (128,128,3) and prob (128,128)); used by planted-pose parity tests only.
     void set_override(int stage, const float* dec, const float* prob, int n);
-    // Host frames (F,H,W,3) uint8 -> device copy owned by the pipeline.
-    const uint8_t* upload_frames(const uint8_t* frames_host, int F, int H, int W);
+    // Host frames (F,H,W,3) uint8 / float32 -> device copy owned by the pipeline.
+    const void* upload_frames(const void* frames_host, bool f32, int F, int H, int W);
     long long launches = 0;
     double box_size = 1.5;   // recognition.py:19 (refined boxes, :110)
     Engine* engine;
@@ -101,17 +110,33 @@ class Pipeline {
     DevBuf<PoseRecord> recs_;
     DevBuf<float> x1_, dec1_, prob1_, x2_, dec2_, prob2_;
     DevBuf<uint8_t> bits1_;       // (D,128,128): bit t = non_gray & prob<th_t ; bit 7 = non_gray
-    DevBuf<int> n_active_;        // per stage-2 chunk
-    DevBuf<double> th_;
+    DevBuf<int> n_active_;        // live candidates per (segment, stage-2 chunk)
+    DevBuf<int> seg_tab_;         // [n_seg + 1] first detection of each segment, then [n_seg + 1] first n_active_ slot
+    std::vector<int> host_seg_;
     DevBuf<uint8_t> xyz_u8_, valid_, pnp_mask_;
     DevBuf<float> obj_, img_;
     DevBuf<PnpProblem> problems_;
     DevBuf<PnpResult> pnp_res_;
-    DevBuf<uint8_t> frames_, det_masks_;
+    DevBuf<uint8_t> frames_[2], det_masks_;
+    int frames_next_ = 0;
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t frames_ready_[2] = {nullptr, nullptr}, frames_free_[2] = {nullptr, nullptr};
     DevBuf<long long> iou_;
     std::vector<float> ov_dec_[2], ov_prob_[2];
     long long pool_px_ = 0;
     std::vector<DetIn> host_dets_;
+    // The kernel sequence of a run has no host-dependent control flow (live counts stay on the device), so it is captured
+    // into a CUDA graph per configuration and replayed: ~150 launches cost one graph launch.
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::map<std::vector<long long>, GraphEntry> graphs_;
+    long long pool_gen_ = 0;
+    DetIn* pinned_dets_ = nullptr;
+    PoseRecord* pinned_recs_ = nullptr;
+    void enqueue(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H, int W,
+                 int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s);
+
+  public:
+    bool use_graph = true;        // P2P_GRAPH=0 launches kernel by kernel
 };
 
 }  // namespace p2p

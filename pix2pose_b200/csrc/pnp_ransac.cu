@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
 
 PnpSolver::PnpSolver() {
     require_device();
+    P2P_CUDA(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(double) * 144 * kHypThreads)));
     P2P_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 }
 PnpSolver::~PnpSolver() {
@@ -432,11 +433,6 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     mark(0);
     {
         const size_t hyp_smem = sizeof(double) * 144 * kHypThreads;
-        static bool attr_set = false;
-        if (!attr_set) {
-            P2P_CUDA(cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hyp_smem)));
-            attr_set = true;
-        }
         const long long total = static_cast<long long>(n_problems) * iters;
         ransac_hyp_kernel<<<static_cast<unsigned>((total + kHypThreads - 1) / kHypThreads), kHypThreads, hyp_smem, s>>>(
             problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters);

@@ -49,6 +49,8 @@ class PnpSolver {
     // Host convenience: one problem, double inputs converted to float32 like OpenCV does.
     void solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,
                     double confidence, PnpResult* out, uint8_t* mask_out);
+    // Allocates the scratch for a batch up front (so that solve_batch can run inside a stream capture).
+    void reserve(int n_problems, int iters) { ensure(n_problems, iters); }
     long long launches = 0;
 
   private:

@@ -20,6 +20,17 @@ def shard_indices(n, rank, world):
     return np.arange(rank, n, world, dtype=np.int64)
 
 
+def shard_by_object(obj_ids, rank, world):
+    """Indices of the detections rank `rank` owns when a multi-object stream is sharded: the stream is ordered by object id
+    (stable) and cut into `world` contiguous ranges of near-equal length, so that a rank sees as few objects as possible
+    and each object's detections form one large sub-batch there (one generator forward per object and rank; SURVEY
+    section 8e: "within a rank, group by object id so one weight set serves a whole sub-batch")."""
+    order = np.argsort(np.asarray(obj_ids), kind="stable")
+    n = len(order)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return np.sort(order[lo:hi])
+
+
 def init(backend=None):
     import torch
     import torch.distributed as dist
@@ -91,3 +102,59 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class AsyncGather:
+    """The per-step result gather taken off the critical path: ``submit`` stages the local (n_local, 16) records in pinned
+    memory and enqueues H2D -> all_gather -> D2H on a side stream without blocking the host; ``result`` (called one step
+    later) waits for that step's event only.  No numpy -> pageable -> .cpu() hop and no implicit barrier inside the step.
+    Falls back to the blocking ``gather_records`` without NCCL (gloo CPU tests, world 1)."""
+
+    def __init__(self, n_local_max, n_total):
+        import torch
+        import torch.distributed as dist
+        self.n_total = n_total
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.nccl = self.world > 1 and dist.get_backend() == "nccl"
+        self.pending = None
+        if self.nccl:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.cap = n_local_max
+            self.host_in = torch.full((self.cap, RECORD), -1.0, dtype=torch.float64).pin_memory()
+            self.dev_in = torch.empty((self.cap, RECORD), dtype=torch.float64, device=dev)
+            self.dev_out = torch.empty((self.world * self.cap, RECORD), dtype=torch.float64, device=dev)
+            self.host_out = torch.empty((self.world * self.cap, RECORD), dtype=torch.float64).pin_memory()
+            self.stream = torch.cuda.Stream(device=dev)
+            self.done = torch.cuda.Event()
+
+    def submit(self, local_records, global_index):
+        import torch
+        import torch.distributed as dist
+        rec = np.array(local_records, np.float64).reshape(-1, RECORD)
+        rec[:, RECORD - 1] = np.asarray(global_index, np.float64)
+        if not self.nccl:
+            self.pending = gather_records(rec, global_index, self.n_total)
+            return
+        if self.pending is not None:
+            self.done.synchronize()          # the staging buffers are reused: the previous gather must have left them
+        self.host_in.fill_(-1.0)
+        self.host_in[: rec.shape[0]] = torch.from_numpy(rec)
+        with torch.cuda.stream(self.stream):
+            self.dev_in.copy_(self.host_in, non_blocking=True)
+            dist.all_gather_into_tensor(self.dev_out, self.dev_in)
+            self.host_out.copy_(self.dev_out, non_blocking=True)
+            self.done.record(self.stream)
+        self.pending = True
+
+    def result(self):
+        """(n_total, 16) records of the last submitted step, ordered by global detection index."""
+        if self.pending is None:
+            return None
+        if not self.nccl:
+            return self.pending
+        self.done.synchronize()
+        allr = self.host_out.numpy()
+        allr = allr[allr[:, RECORD - 1] >= 0]
+        out = np.zeros((self.n_total, RECORD))
+        out[allr[:, RECORD - 1].astype(np.int64)] = allr
+        return out

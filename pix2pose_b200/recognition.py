@@ -25,7 +25,8 @@ class _Det(ctypes.Structure):
     _fields_ = [("frame", ctypes.c_int), ("skip", ctypes.c_int), ("bbox", ctypes.c_int * 4), ("box1", ctypes.c_int * 12),
                 ("fu", ctypes.c_double), ("fv", ctypes.c_double), ("uc", ctypes.c_double), ("vc", ctypes.c_double),
                 ("scale", ctypes.c_double * 3), ("ct", ctypes.c_double * 3),
-                ("pool_off", ctypes.c_longlong), ("cap_px", ctypes.c_int), ("pad", ctypes.c_int)]
+                ("pool_off", ctypes.c_longlong), ("cap_px", ctypes.c_int), ("seg", ctypes.c_int),
+                ("th_o", ctypes.c_double * 8), ("th_i", ctypes.c_double)]
 
 
 class _Pose(ctypes.Structure):
@@ -62,7 +63,7 @@ def _get_boxes(box_size, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
 
 DET_DTYPE = np.dtype([("frame", "<i4"), ("skip", "<i4"), ("bbox", "<i4", 4), ("box1", "<i4", 12), ("fu", "<f8"), ("fv", "<f8"),
                       ("uc", "<f8"), ("vc", "<f8"), ("scale", "<f8", 3), ("ct", "<f8", 3), ("pool_off", "<i8"), ("cap_px", "<i4"),
-                      ("pad", "<i4")], align=True)
+                      ("seg", "<i4"), ("th_o", "<f8", 8), ("th_i", "<f8")], align=True)
 POSE_DTYPE = np.dtype([("R", "<f8", 9), ("t", "<f8", 3), ("frac_inlier", "<f8"), ("status", "<i4"), ("n_inliers", "<i4"),
                        ("best_cand", "<i4"), ("n_cand", "<i4"), ("bbox_t", "<i4", 4), ("best_box", "<i4", 12), ("n_init", "<i4"),
                        ("mask_all_true", "<i4"), ("cand_base", "<i4"), ("pad", "<i4")], align=True)
@@ -92,8 +93,8 @@ def _get_boxes_batch(box_size, bboxes, v_max, u_max):
 class PoseBatchResult:
     """Result of ``est_pose_batch``: struct-of-arrays view plus lazy crop access."""
 
-    def __init__(self, owner, poses, n):
-        self._owner, self._poses, self.n = owner, poses, n
+    def __init__(self, owner, poses, n, run_id):
+        self._owner, self._poses, self.n, self._run_id = owner, poses, n, run_id
         a = np.frombuffer(poses, dtype=POSE_DTYPE, count=max(n, 1))[:n]
         self.status = a["status"].copy()
         self.R = a["R"].reshape(n, 3, 3).copy()
@@ -113,8 +114,9 @@ class PoseBatchResult:
         return rec
 
     def crop(self, d):
-        """(img_pred uint8 (h,w,3), valid_mask bool (h,w), box) of detection d's winning candidate."""
-        return self._owner._fetch_crop(d, self._poses[d])
+        """(img_pred uint8 (h,w,3), valid_mask bool (h,w), box) of detection d's winning candidate.  Reads the pipeline's
+        candidate pools, so it must be called before the next run of the (shared) pipeline -- a stale result raises."""
+        return self._owner._fetch_crop(d, self._poses[d], self._run_id)
 
     def mask_iou(self, masks):
         """Device-side mask IoU ingredients (tools/5_evaluation_bop_basic.py:307-316): ``masks`` (n,H,W) bool/uint8 detector
@@ -125,7 +127,7 @@ class PoseBatchResult:
             raise ValueError("masks must be (n,H,W) with n = %d detections, got %s" % (self.n, m.shape))
         out = np.zeros((self.n, 2), np.int64)
         if self.n:
-            _lib.check(_lib.lib().p2p_pipeline_mask_iou(self._owner._pipe, m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.n,
+            _lib.check(_lib.lib().p2p_pipeline_mask_iou(self._owner._live_pipe(self._run_id), m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.n,
                                                         m.shape[1], m.shape[2], out.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
         return out[:, 0].copy(), out[:, 1].copy()
 
@@ -151,10 +153,8 @@ class pix2pose():
         else:
             raise ValueError("backbone must be 'paper' or 'resnet50'")
         self.generator_train.load_weights(weight_fn)
-        self._pipe = None
-        self._pipe_key = None
         self._max_dets = int(max_dets)
-        self._last = None
+        self._last_run = None
 
     # ------------------------------------------------------------------------------------------------
     def get_boxes(self, bbox, v_max, u_max, ct=np.array([-1]), max_w=9999):
@@ -163,32 +163,48 @@ class pix2pose():
     # The device pipeline (stage buffers, candidate pools, PnP scratch) does not depend on the object: all
     # pix2pose instances that share an engine and a threshold count share ONE pipeline, like the reference's
     # per-object models share one TF session (tools/5_evaluation_bop_basic.py:112-114).
-    _shared_pipes = {}
+    _shared_pipes = {}     # (engine id, n thresholds) -> {"h": handle, "cap": max_dets, "eng": engine, "run": run counter, "old": [...]}
+
+    def _entry(self):
+        eng = self.generator_train.engine
+        return pix2pose._shared_pipes.get((id(eng), len(self.th_o)))
 
     def _pipeline(self, n):
+        """The shared device pipeline, grown if `n` detections do not fit.  A pipeline that is outgrown is NOT destroyed while
+        the process lives (results and other objects may still hold buffers in it: it is parked in the entry's "old" list and
+        its results are invalidated through the run counter); every access goes through the shared entry, never through a
+        cached handle."""
         eng = self.generator_train.engine
         key = (id(eng), len(self.th_o))
         ent = pix2pose._shared_pipes.get(key)
         want = max(self._max_dets, n)
-        if ent is None or ent[1] < n:
+        if ent is None or ent["cap"] < n:
             h = ctypes.c_void_p()
             _lib.check(_lib.lib().p2p_pipeline_create(eng.handle, want, len(self.th_o), ctypes.byref(h)))
-            if ent is not None:
-                _lib.lib().p2p_pipeline_destroy(ent[0])
-            ent = (h, want, eng)          # keeps the engine alive as long as the pipeline
+            old = [] if ent is None else ent["old"] + [ent["h"]]
+            ent = {"h": h, "cap": want, "eng": eng, "run": 0 if ent is None else ent["run"] + 1, "old": old}
             pix2pose._shared_pipes[key] = ent
-        self._pipe = ent[0]
-        _lib.check(_lib.lib().p2p_pipeline_set_box_size(self._pipe, float(self.box_size)))   # pipelines are shared by objects
-        return self._pipe
+        _lib.check(_lib.lib().p2p_pipeline_set_box_size(ent["h"], float(self.box_size)))   # pipelines are shared by objects
+        return ent["h"]
 
-    def _release_pipe(self):
-        self._pipe = None
+    def _live_pipe(self, run_id=None):
+        """Handle of the shared pipeline for reading back the buffers of run `run_id` (default: this object's last run);
+        raises when another run (of any object sharing the pipeline) has overwritten them since."""
+        ent = self._entry()
+        if ent is None:
+            raise RuntimeError("no pipeline run yet")
+        want = self._last_run if run_id is None else run_id
+        if want is None or ent["run"] != want:
+            raise RuntimeError("stale result: the shared device pipeline has run again (run %s, result of run %s); fetch crops / "
+                               "masks before the next est_pose call" % (ent["run"], want))
+        return ent["h"]
 
     @property
     def launch_count(self):
         n = self.generator_train.engine.launch_count
-        if self._pipe is not None:
-            n += int(_lib.lib().p2p_pipeline_launch_count(self._pipe))
+        ent = self._entry()
+        if ent is not None:
+            n += int(_lib.lib().p2p_pipeline_launch_count(ent["h"]))
         return n
 
     def _make_dets(self, shape_hw, bboxes, frame_ids, camKs):
@@ -213,6 +229,10 @@ class pix2pose():
             a["fu"], a["fv"], a["uc"], a["vc"] = Ks[:, 0, 0], Ks[:, 1, 1], Ks[:, 0, 2], Ks[:, 1, 2]
         a["scale"] = np.asarray(self.obj_scale, np.float64)
         a["ct"] = np.asarray(self.obj_ct, np.float64)
+        th = np.zeros(8)
+        th[:len(self.th_o)] = np.asarray(self.th_o, np.float64).reshape(-1)   # cfg_tless_paper.json nests them: [[0.1]]
+        a["th_o"] = th
+        a["th_i"] = float(self.th_i)
         return dets
 
     def est_pose_batch(self, frames, bboxes, frame_ids=None, camKs=None, frames_dev=None):
@@ -223,6 +243,7 @@ class pix2pose():
         Returns a ``PoseBatchResult``; ``status``: 1 pose found, 0 the reference would return its -1
         sentinels, -2 the crop was smaller than 5 px (recognition.py:78)."""
         n = len(bboxes)
+        f32 = False
         if frames_dev is not None:
             dev, F, H, W, pipe0 = frames_dev
         else:
@@ -230,28 +251,35 @@ class pix2pose():
             if frames.ndim == 3:
                 frames = frames[None]
             if frames.dtype != np.uint8:
-                # the ICP driver passes float32 images holding 0..255 (5_evaluation_bop_icp3d.py:369)
-                frames = frames.astype(np.uint8)
+                # the ICP driver passes a float32 image (0..255, invalid-depth pixels scaled by 0.1: non-integers;
+                # 5_evaluation_bop_icp3d.py:369-370); numpy promotes `rgb - [128,128,128]` to float64 on it, so the crops are
+                # cut from the float values (float64 input would be rounded to float32 here: the reference never passes it)
+                frames, f32 = frames.astype(np.float32), True
             frames = np.ascontiguousarray(frames)
             F, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
         if frame_ids is None:
             frame_ids = np.zeros(n, np.int64)
         dets = self._make_dets((H, W), bboxes, frame_ids, camKs)
         poses = (_Pose * max(n, 1))()
-        th = np.ascontiguousarray(np.asarray(self.th_o, np.float64))
+        th = np.ascontiguousarray(np.asarray(self.th_o, np.float64).reshape(-1))
         pipe = self._pipeline(n)
+        ent = self._entry()
         thp = th.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        ent["run"] += 1
+        self._last_run = ent["run"]
         if frames_dev is not None:
-            if pipe0 is not pipe:
+            if pipe0.value != pipe.value:
                 raise RuntimeError("frames_dev belongs to a pipeline that was rebuilt; upload the frames again")
             _lib.check(_lib.lib().p2p_pipeline_run_device(pipe, self.generator_train._model, dev, F, H, W, dets, n, thp,
                                                           float(self.th_i), 5.0, 100, 0.99, poses))
+        elif f32:
+            _lib.check(_lib.lib().p2p_pipeline_run_f32(pipe, self.generator_train._model, _lib.fptr(frames), F, H, W, dets, n,
+                                                       thp, float(self.th_i), 5.0, 100, 0.99, poses))
         else:
             _lib.check(_lib.lib().p2p_pipeline_run(
                 pipe, self.generator_train._model, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), F, H, W, dets, n,
                 thp, float(self.th_i), 5.0, 100, 0.99, poses))
-        self._last = (dets, poses, n, (H, W))
-        return PoseBatchResult(self, poses, n)
+        return PoseBatchResult(self, poses, n, self._last_run)
 
     def upload_frames(self, frames, n_dets=1):
         """Copies (F,H,W,3) uint8 frames into the pipeline's device buffer; returns an opaque handle for
@@ -265,13 +293,13 @@ class pix2pose():
                                                          frames.shape[0], frames.shape[1], frames.shape[2], ctypes.byref(dev)))
         return (dev, frames.shape[0], frames.shape[1], frames.shape[2], pipe)
 
-    def _fetch_crop(self, d, pose):
+    def _fetch_crop(self, d, pose, run_id=None):
         bx = list(pose.best_box)
         h, w = max(bx[5] - bx[4], 0), max(bx[7] - bx[6], 0)
         xyz = np.zeros((h, w, 3), np.uint8)
         mask = np.zeros((h, w), np.uint8)
         if h * w > 0:
-            _lib.check(_lib.lib().p2p_pipeline_fetch_crop(self._pipe, d, ctypes.byref(pose),
+            _lib.check(_lib.lib().p2p_pipeline_fetch_crop(self._live_pipe(run_id), d, ctypes.byref(pose),
                                                           xyz.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
                                                           mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
         if pose.mask_all_true:
@@ -281,18 +309,17 @@ class pix2pose():
     def debug_fetch(self, what, index):
         """Parity hook: float buffers of the last run (1 dec1, 2 dec2, 3 x1, 4 x2, 5 prob1, 6 prob2)."""
         out = np.zeros((128, 128, 3) if what <= 4 else (128, 128), np.float32)
-        _lib.check(_lib.lib().p2p_pipeline_fetch_buffer(self._pipe, what, index, _lib.fptr(out)))
+        _lib.check(_lib.lib().p2p_pipeline_fetch_buffer(self._live_pipe(), what, index, _lib.fptr(out)))
         return out
 
     def debug_override(self, stage, decode, prob, n_dets=1):
         """Parity hook: the next run uses these arrays instead of the network outputs of `stage`."""
         decode, prob = _lib.as_f32(decode), _lib.as_f32(prob)
-        self._pipeline(n_dets)
-        _lib.check(_lib.lib().p2p_pipeline_debug_override(self._pipe, stage, _lib.fptr(decode), _lib.fptr(prob), decode.shape[0]))
+        _lib.check(_lib.lib().p2p_pipeline_debug_override(self._pipeline(n_dets), stage, _lib.fptr(decode), _lib.fptr(prob), decode.shape[0]))
 
     def _fetch_pred(self, stage, index, zero_gray):
         dec = np.zeros((128, 128, 3), np.float32)
-        _lib.check(_lib.lib().p2p_pipeline_fetch_decode(self._pipe, stage, index, _lib.fptr(dec)))
+        _lib.check(_lib.lib().p2p_pipeline_fetch_decode(self._live_pipe(), stage, index, _lib.fptr(dec)))
         if zero_gray:
             dec[np.linalg.norm(dec, axis=2) < 0.3] = 0           # recognition.py:137-139
         return np.clip((dec + 1) / 2, 0, 1)                       # :85-87 / :141-143

@@ -28,6 +28,10 @@ class FakeLib:
         msk[0], msk[1], cnt[0], cnt[1] = 7.0, 0.1, 32, 3
         return 0
     def p2p_flops_per_crop(self, bb): return 10.7e9
+    def p2p_engine_prof_begin(self, eng): return 0
+    def p2p_engine_prof_end(self, eng, msk, cnt):
+        msk[0], msk[1], cnt[0], cnt[1] = 56.0, 0.8, 256, 24      # two profiled steps
+        return 0
 
 import pix2pose_b200._lib as _lib
 _lib.lib = lambda: FakeLib()
@@ -41,6 +45,11 @@ D.barrier = lambda: None
 D.max_over_ranks = lambda v: v
 D.gather_records = lambda rec, idx, n: rec
 D.shutdown = lambda: None
+class FakeGather:
+    def __init__(self, cap, n_total): self.n, self.last = n_total, None
+    def submit(self, rec, idx): self.last = np.zeros((self.n, 16))
+    def result(self): return self.last
+D.AsyncGather = FakeGather
 
 class FakeRes:
     def __init__(self, n):
@@ -65,7 +74,7 @@ import bench
 bench.ClockSampler.run = lambda self: None
 class FakeOra:
     def est_pose(self, frame, roi): return (None, np.zeros(1), None, None, 0.5, None)
-bench.make_cpu_port = lambda: FakeOra()
+bench.make_cpu_port = lambda cfg=3: FakeOra()
 sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "3", "--cpu-sample", "4"]
 print("library banner that must not reach stdout")
 os.write(1, b"raw fd-1 write before main\n")
@@ -91,7 +100,10 @@ def test_bench_emits_exactly_one_json_line_with_the_contract_keys(world, tmp_pat
     assert d["n_gpus"] == world and d["steps"] == 2 and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["ms_per_step"] == pytest.approx(40.0) and d["value"] == pytest.approx(256 * world / 0.040)
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
-    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and "workload" in d["config"]
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "step_frac"} and "workload" in d["config"]
+    assert d["config"]["workload"].startswith("config3")          # the default stays the configuration the metric is quoted on
+    assert d["roofline"]["achieved"] == pytest.approx(10.7e9 * 1024 / 28e-3 / 1e12)
+    assert d["roofline"]["step_frac"] < d["roofline"]["frac"]
     assert d["gpu_launches"] == 300
     if world == 1:
         assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["cores"] >= 1

@@ -22,6 +22,10 @@ rec = np.zeros((len(idx), 16))
 rec[:, 0] = idx * 10.0 + 1          # a per-detection payload derived from the global index
 rec[:, 14] = 1
 out = D.gather_records(rec, idx, n)
+g = D.AsyncGather((n + world - 1) // world + 1, n)          # without NCCL: the blocking gather behind the same interface
+assert g.result() is None
+g.submit(rec, idx)
+assert np.array_equal(g.result(), out)
 assert out.shape == (n, 16)
 assert np.array_equal(out[:, 15], np.arange(n)), out[:, 15]
 assert np.array_equal(out[:, 0], np.arange(n) * 10.0 + 1)
@@ -39,6 +43,40 @@ def test_shard_indices_partition():
             allidx = np.sort(np.concatenate(parts)) if parts else np.array([])
             assert np.array_equal(allidx, np.arange(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_shard_by_object_keeps_object_groups_together():
+    """Multi-object streams (BASELINE configs 4 / 5): every detection is owned by exactly one rank, ranks are balanced to
+    within one detection, and a rank sees a contiguous run of object ids (LM-O on 8 GPUs: exactly one object per rank)."""
+    lmo = [1, 5, 6, 8, 9, 10, 11, 12]
+    oids = np.array([lmo[i % 8] for i in range(512)])
+    for world in (1, 2, 4, 8):
+        parts = [D.shard_by_object(oids, r, world) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(512))
+        assert all(len(p) == 512 // world for p in parts)
+        assert all(len(np.unique(oids[p])) == 8 // world for p in parts)
+    tless = np.array([1 + i % 30 for i in range(2000)])
+    parts = [D.shard_by_object(tless, r, 8) for r in range(8)]
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(2000))
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert max(len(np.unique(tless[p])) for p in parts) <= 5          # 30 objects over 8 ranks: 3.75 -> at most 5 groups per rank
+    for p in parts:
+        assert np.array_equal(p, np.sort(p))                           # stream order is kept inside a rank
+
+
+def test_bench_workloads_shard_consistently():
+    """bench.py's config 4 (strong, 512 fixed) and config 5 (weak, 250 per GPU) workloads: the ranks' detections partition
+    the global stream and frame indices stay inside each rank's own frame batch."""
+    import bench
+    for cfg, world in ((4, 1), (4, 8), (5, 2), (5, 8)):
+        seen = []
+        for r in range(world):
+            frames, rois, fids, oids, gidx, total = bench.workload(cfg, r, world)
+            assert len(rois) == len(fids) == len(oids) == len(gidx) and fids.max() < len(frames)
+            assert frames.shape[1:] == ((480, 640, 3) if cfg == 4 else (540, 720, 3))
+            seen.append(gidx)
+        allidx = np.sort(np.concatenate(seen))
+        assert np.array_equal(allidx, np.arange(512 if cfg == 4 else 250 * world))
 
 
 def test_single_process_gather():

@@ -61,6 +61,88 @@ def test_stagewise_bit_parity_with_same_network_outputs(rec, frame, roi):
         assert got[2].shape == (3, 3) and got[3].shape == (3,)
 
 
+# The configurations the reference ships: thresholds, backbone, frame size and frame dtype.
+K_TLESS = np.array([[1075.65, 0, 360.0], [0, 1073.90, 270.0], [0, 0, 1]])
+SHIPPED = {
+    "cfg_bop2020": dict(th_outlier=[0.2, 0.3, 0.35], th_inlier=0.2, backbone="resnet50", hw=(480, 640), K=K_LM),          # cfg_bop2020.json:2,8-9
+    "cfg_bop2019_paper": dict(th_outlier=[0.15, 0.25, 0.35], th_inlier=0.15, backbone="paper", hw=(480, 640), K=K_LM),     # cfg_bop2019.json:2,8-9
+    "cfg_tless_paper": dict(th_outlier=[[0.3]], th_inlier=0.1, backbone="paper", hw=(540, 720), K=K_TLESS),               # cfg_tless_paper.json:12-13 via 5_evaluation_bop_basic.py:217
+    "ros_config": dict(th_outlier=[0.1, 0.2, 0.3, 0.4], th_inlier=0.15, backbone="resnet50", hw=(480, 640), K=K_LM),       # ros_kinetic/ros_config.json:7-9
+    "icp3d_float32": dict(th_outlier=[0.15, 0.25, 0.35], th_inlier=0.15, backbone="resnet50", hw=(480, 640), K=K_LM, f32=True),  # 5_evaluation_bop_icp3d.py:369-370
+}
+
+
+@pytest.mark.parametrize("name", sorted(SHIPPED))
+def test_stagewise_bit_parity_in_shipped_configurations(name):
+    """Same bit-parity bar as above for every configuration the reference ships: one threshold (nested list, as the T-LESS
+    config hands it over), four thresholds, the 2020 thresholds, 720x540 frames, the paper backbone, and the float32 frame
+    of the ICP driver (invalid-depth pixels scaled by 0.1, i.e. non-integer pixel values)."""
+    from oracle.recognition_oracle import Pix2PoseOracle
+    from pix2pose_b200.recognition import pix2pose
+    c = SHIPPED[name]
+    H, W = c["hw"]
+    r = pix2pose(W_synth(c["backbone"]), c["K"], W, H, OBJ, backbone=c["backbone"], capacity=16, max_dets=16,
+                 th_outlier=c["th_outlier"], th_inlier=c["th_inlier"])
+    rng = np.random.RandomState(3)
+    f = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    f[H // 3:2 * H // 3, W // 3:2 * W // 3] = (f[H // 3:2 * H // 3, W // 3:2 * W // 3] // 4 + 100).astype(np.uint8)
+    if c.get("f32"):
+        f = f.astype(np.float32)
+        bad = rng.rand(H, W) < 0.3
+        f[bad] = 0.1 * f[bad]                                                    # 5_evaluation_bop_icp3d.py:370
+    ora = Pix2PoseOracle(r.generator_train, c["K"], W, H, OBJ, th_outlier=c["th_outlier"], th_inlier=c["th_inlier"])
+    n_cands = 0
+    for roi in ([H // 2 - 43, W // 2 - 43, H // 2 + 43, W // 2 + 43], [-20, -10, 90, 120], [H - 180, W - 230, H - 10, W + 20]):
+        ora.trace = {}
+        want = ora.est_pose(f, np.array(roi))
+        got = r.est_pose(f, np.array(roi))
+        assert list(got[5]) == list(want[5]), (name, roi)
+        assert np.array_equal(r.debug_fetch(3, 0), ora.trace["x1"].astype(np.float32)), (name, roi)
+        for k in range(len(ora.trace["x2"])):
+            assert np.array_equal(r.debug_fetch(4, k), ora.trace["x2"][k].astype(np.float32)), (name, roi, k)
+        for cd in ora.trace["cands"]:
+            xyz, mask, _ = _cand_crop(r, cd["cid"], cd["box"])
+            assert np.array_equal(xyz, cd["xyz_u8"]) and np.array_equal(mask, np.asarray(cd["valid_mask"], bool)), (name, roi, cd["cid"])
+            n_cands += 1
+        assert isinstance(got[1], int) == isinstance(want[1], int)
+        if not isinstance(want[1], int):
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[4] == want[4]
+            assert np.abs(got[2] - want[2]).max() <= 1e-9 and np.abs(got[3] - want[3]).max() <= 1e-6 * np.abs(want[3]).max()
+    assert n_cands > 0, name
+
+
+def W_synth(backbone):
+    return W.synthetic_weights(backbone, 1)
+
+
+def test_refined_box_centre_minus_one_quirk(rec, frame):
+    """recognition.py:29 treats ``ct[0] == -1`` as "no centre given"; the stage-2 call (:110) passes the computed centre
+    ``[cy_m, cx_m]``, so a mask centroid that lands on row -1 (ROIs at the top edge) silently falls back to the centre of
+    the 128-space bbox.  Planted stage-1 maps put the centroid exactly there; the device path must build the same refined
+    box as the oracle (= the reference's behaviour)."""
+    from oracle.recognition_oracle import Pix2PoseOracle
+    from tests.planted import PlantedGenerator
+    roi = np.array([-40, 260, 40, 340])                     # cy_o = 0
+    dec = np.zeros((1, 128, 128, 3), np.float32)
+    dec[0, 30:95, 20:108] = 0.5                            # rows 30..94: mean 62 -> cy_m = int(62 - 63.5 + 0) = int(-1.5) = -1
+    prob = np.full((1, 128, 128, 1), 0.05, np.float32)
+    s2 = (np.tile(dec, (3, 1, 1, 1)), np.tile(prob, (3, 1, 1, 1)))
+    ora = Pix2PoseOracle(PlantedGenerator((dec, prob), s2), K_LM, 640, 480, OBJ, **TH)
+    ora.trace = {}
+    want = ora.est_pose(frame, roi)
+    assert len(ora.trace["boxes2"]) == 3
+    rec.debug_override(1, dec, prob)
+    rec.debug_override(2, s2[0], s2[1])
+    got = rec.est_pose(frame, roi)
+    assert list(got[5]) == list(want[5])
+    for k in range(len(ora.trace["x2"])):
+        assert np.array_equal(rec.debug_fetch(4, k), ora.trace["x2"][k].astype(np.float32)), k
+    # and the quirk really was exercised: with the centre honoured the box would sit one row higher
+    from oracle.recognition_oracle import get_boxes
+    b = ora.trace["boxes2"][0]
+    assert (b[0] + b[1]) // 2 != -1
+
+
 def test_non_default_box_size_matches_oracle(frame):
     """box_size is a constructor argument of the reference (recognition.py:10, :19); the device-side refined-box
     arithmetic follows it (p2p_pipeline_set_box_size)."""
@@ -211,3 +293,57 @@ def test_device_mask_iou_matches_numpy(rec, frame):
             full[bx[4]:bx[5], bx[6]:bx[7]] = m
         assert inter[i] == np.sum(full & masks[i]) and union[i] == np.sum(full | masks[i]), i
     assert (res.status == 1).any()
+
+
+def test_tless_like_stream_per_object_thresholds():
+    """SURVEY section 8d config 5 in miniature: 720x540 frames, the paper backbone, one outlier threshold PER OBJECT handed over
+    as a nested list (cfg_tless_paper.json:12, 5_evaluation_bop_basic.py:217), all objects' detections in one device run:
+    every detection gets exactly what its own object's recogniser returns for it alone."""
+    from pix2pose_b200.stream import MultiObjectRecognizer
+    ths = {1: [[0.1]], 4: [[0.3]], 5: [[0.2]]}
+    objs = {1: np.array([50., 40., 60., 0., 0., 0.]), 4: np.array([30., 30., 80., 1., -2., 3.]), 5: np.array([45., 45., 20., 0., 5., 0.])}
+    wts = {o: W.synthetic_weights("paper", o) for o in ths}
+    multi = MultiObjectRecognizer(wts, K_TLESS, 720, 540, objs, th_outlier=ths, th_inlier=0.1, backbone="paper", capacity=16, max_dets=32)
+    rng = np.random.RandomState(8)
+    frames = rng.randint(0, 256, (2, 540, 720, 3)).astype(np.uint8)
+    rois, oids, fids = [], [], []
+    for i in range(14):
+        cy, cx, h, w = rng.randint(80, 460), rng.randint(80, 640), rng.randint(50, 140), rng.randint(50, 140)
+        rois.append([cy - h // 2, cx - w // 2, cy + h // 2, cx + w // 2]); oids.append([1, 4, 5, 9][i % 4]); fids.append(i % 2)
+    rec, status = multi.est_pose_stream(frames, rois, oids, fids)
+    assert rec.shape == (14, 16) and np.array_equal(rec[:, 15], np.arange(14))
+    assert all(status[i] == -3 for i in range(14) if oids[i] == 9)
+    for i in range(14):
+        if oids[i] == 9:
+            continue
+        one = multi.models[oids[i]].est_pose_batch(frames[fids[i]], [rois[i]])
+        assert one.status[0] == status[i], i
+        assert np.array_equal(one.R[0].ravel(), rec[i, :9]) and np.array_equal(one.t[0], rec[i, 9:12]), i
+        assert one.n_inliers[0] == rec[i, 12] and one.frac_inlier[0] == rec[i, 13]
+    assert (status == 1).sum() >= 3
+
+
+def test_stale_result_access_raises(rec, frame):
+    """The device pipeline is shared by all objects: reading a result's crops after another run would return that run's
+    pool data, so it must raise instead."""
+    res = rec.est_pose_batch(frame, [np.array(ROIS[0])])
+    assert res.status[0] == 1
+    res.crop(0)
+    rec.est_pose_batch(frame, [np.array(ROIS[1])])
+    with pytest.raises(RuntimeError):
+        res.crop(0)
+    with pytest.raises(RuntimeError):
+        res.mask_iou(np.zeros((1, 480, 640), bool))
+
+
+def test_graph_replay_equals_plain_launches(rec, frame):
+    """The captured CUDA graph of a run and the kernel-by-kernel path give identical records, call after call."""
+    import os
+    rois = [np.array(r) for r in ROIS]
+    a = rec.est_pose_batch(frame, rois)
+    b = rec.est_pose_batch(frame, rois)          # replay of the graph captured by the first call
+    assert np.array_equal(a.R, b.R) and np.array_equal(a.t, b.t) and np.array_equal(a.status, b.status)
+    assert np.array_equal(a.n_inliers, b.n_inliers) and np.array_equal(a.bbox_t, b.bbox_t)
+    l0 = rec.launch_count
+    rec.est_pose_batch(frame, rois)
+    assert rec.launch_count - l0 > 100           # replays still count their kernels (bench.py's gpu_launches)
