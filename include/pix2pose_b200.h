@@ -153,6 +153,9 @@ P2P_API int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const floa
  * refined boxes :110).  Applies to the following runs; default 1.5. */
 P2P_API int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size);
 P2P_API long long p2p_pipeline_launch_count(const p2p_pipeline_t* p);
+/* Measurement: device milliseconds the generator forwards (recognition.py:84 and :129) of the LAST run took, from CUDA
+ * event nodes recorded around them inside the run itself (they are part of the captured graph). */
+P2P_API int p2p_pipeline_forward_ms(p2p_pipeline_t* p, double* ms);
 
 /* Measurement helper: uploads x (n <= capacity crops, host), then times `iters` device-resident
  * forwards after `warmup` untimed ones with CUDA events on the engine's stream; *ms_per_iter is

@@ -214,6 +214,12 @@ int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size) {
         p->p->box_size = box_size;
     });
 }
+int p2p_pipeline_forward_ms(p2p_pipeline_t* p, double* ms) {
+    return guarded([&] {
+        P2P_CHECK(p && ms, "NULL argument");
+        *ms = p->p->forward_ms();
+    });
+}
 long long p2p_pipeline_launch_count(const p2p_pipeline_t* p) { return p ? p->p->launches + p->p->pnp.launches : 0; }
 
 int p2p_time_forward(p2p_engine_t* e, const p2p_model_t* m, const float* x, int n, int warmup, int iters,

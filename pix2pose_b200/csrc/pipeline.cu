@@ -581,6 +581,7 @@ Pipeline::~Pipeline() {
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (pinned_dets_) cudaFreeHost(pinned_dets_);
     if (pinned_recs_) cudaFreeHost(pinned_recs_);
+    for (auto e : fwd_ev_) cudaEventDestroy(e);
     if (copy_stream_) {
         cudaStreamDestroy(copy_stream_);
         for (auto& e : frames_ready_) cudaEventDestroy(e);
@@ -608,12 +609,25 @@ void Pipeline::enqueue(const Model* const* models, const int* seg_counts, int n_
     if (frames_f32) crop_resize_kernel<false, float><<<dim3(n, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
     else crop_resize_kernel<false, uint8_t><<<dim3(n, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
     P2P_CUDA(cudaGetLastError());
+    // The generator forwards are bracketed by event-record nodes (they are part of the captured graph): after a run,
+    // forward_ms() is the device time the tcgen05 generator spent in it -- bench.py's live roofline numerator.
+    n_fwd_ev_ = 0;
+    auto fwd_mark = [&]() {
+        if (n_fwd_ev_ == static_cast<int>(fwd_ev_.size())) {
+            cudaEvent_t e;
+            P2P_CUDA(cudaEventCreate(&e));
+            fwd_ev_.push_back(e);
+        }
+        P2P_CUDA(cudaEventRecord(fwd_ev_[n_fwd_ev_++], s));
+    };
+    fwd_mark();
     for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg)
         for (int b = 0; b < seg_counts[sg]; b += cap) {
             const int nb = std::min(cap, seg_counts[sg] - b);
             const size_t at = static_cast<size_t>(d0 + b);
             engine->forward(*models[sg], x1_.p + at * 16384 * 3, nb, dec1_.p + at * 16384 * 3, prob1_.p + at * 16384, nullptr, s);
         }
+    fwd_mark();
     if (!ov_dec_[0].empty()) {   // parity hook (never inside a captured graph)
         P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
         P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -629,6 +643,7 @@ void Pipeline::enqueue(const Model* const* models, const int* seg_counts, int n_
     if (frames_f32) crop_resize_kernel<true, float><<<dim3(C, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
     else crop_resize_kernel<true, uint8_t><<<dim3(C, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
     P2P_CUDA(cudaGetLastError());
+    fwd_mark();
     for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg) {
         const int Cs = seg_counts[sg] * n_th;
         const int c0 = host_seg_[n_seg + 1 + sg];
@@ -639,6 +654,7 @@ void Pipeline::enqueue(const Model* const* models, const int* seg_counts, int n_
                             n_active_.p + c0 + j, s);
         }
     }
+    fwd_mark();
     if (!ov_dec_[1].empty()) {
         P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
         P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -748,9 +764,22 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
         enqueue(models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
     }
     if (fslot >= 0) P2P_CUDA(cudaEventRecord(frames_free_[fslot], s));
+    last_n_fwd_ev_ = 4;
     P2P_CUDA(cudaMemcpyAsync(pinned_recs_, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
     P2P_CUDA(cudaStreamSynchronize(s));
     memcpy(out, pinned_recs_, sizeof(PoseRecord) * n);
+}
+
+double Pipeline::forward_ms() {
+    // events 0-1 bracket the stage-1 forwards, 2-3 the stage-2 forwards of the last run
+    P2P_CHECK(fwd_ev_.size() >= 4 && last_n_fwd_ev_ == 4, "forward_ms: no run yet");
+    double tot = 0;
+    for (int i = 0; i + 1 < 4; i += 2) {
+        float ms = 0;
+        P2P_CUDA(cudaEventElapsedTime(&ms, fwd_ev_[i], fwd_ev_[i + 1]));
+        tot += ms;
+    }
+    return tot;
 }
 
 void Pipeline::fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out) {

@@ -96,6 +96,8 @@ class Pipeline {
     void set_override(int stage, const float* dec, const float* prob, int n);
     // Host frames (F,H,W,3) uint8 / float32 -> device copy owned by the pipeline.
     const void* upload_frames(const void* frames_host, bool f32, int F, int H, int W);
+    // Device milliseconds the generator forwards of the last run took (stage 1 + stage 2; event nodes inside the run).
+    double forward_ms();
     long long launches = 0;
     double box_size = 1.5;   // recognition.py:19 (refined boxes, :110)
     Engine* engine;
@@ -130,6 +132,8 @@ class Pipeline {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     std::map<std::vector<long long>, GraphEntry> graphs_;
     long long pool_gen_ = 0;
+    std::vector<cudaEvent_t> fwd_ev_;
+    int n_fwd_ev_ = 0, last_n_fwd_ev_ = 0;
     DetIn* pinned_dets_ = nullptr;
     PoseRecord* pinned_recs_ = nullptr;
     void enqueue(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H, int W,

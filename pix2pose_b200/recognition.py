@@ -199,6 +199,12 @@ class pix2pose():
                                "masks before the next est_pose call" % (ent["run"], want))
         return ent["h"]
 
+    def last_forward_ms(self):
+        """Device milliseconds the generator forwards of the shared pipeline's last run took (bench.py's roofline numerator)."""
+        ms = ctypes.c_double()
+        _lib.check(_lib.lib().p2p_pipeline_forward_ms(self._entry()["h"], ctypes.byref(ms)))
+        return ms.value
+
     @property
     def launch_count(self):
         n = self.generator_train.engine.launch_count

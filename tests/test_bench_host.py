@@ -61,6 +61,7 @@ class FakeRec:
     def __init__(self, *a, **k):
         self.generator_train = types.SimpleNamespace(engine=types.SimpleNamespace(handle=None), _model=None)
     def upload_frames(self, frames, n): return object()
+    def last_forward_ms(self): return 28.0
     def est_pose_batch(self, frames, rois, fids, frames_dev=None):
         FakeRec.launch_count += 150
         return FakeRes(len(rois))

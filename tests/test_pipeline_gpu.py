@@ -102,7 +102,9 @@ def test_stagewise_bit_parity_in_shipped_configurations(name):
             assert np.array_equal(r.debug_fetch(4, k), ora.trace["x2"][k].astype(np.float32)), (name, roi, k)
         for cd in ora.trace["cands"]:
             xyz, mask, _ = _cand_crop(r, cd["cid"], cd["box"])
-            assert np.array_equal(xyz, cd["xyz_u8"]) and np.array_equal(mask, np.asarray(cd["valid_mask"], bool)), (name, roi, cd["cid"])
+            assert np.array_equal(xyz, cd["xyz_u8"]), (name, roi, cd["cid"])
+            if not isinstance(cd["valid_mask"], int):         # -1: PnP found no consensus (recognition.py:219), no mask to compare
+                assert np.array_equal(mask, np.asarray(cd["valid_mask"], bool)), (name, roi, cd["cid"])
             n_cands += 1
         assert isinstance(got[1], int) == isinstance(want[1], int)
         if not isinstance(want[1], int):
