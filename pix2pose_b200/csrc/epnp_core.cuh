@@ -185,39 +185,37 @@ P2P_HD inline double cv_hypot(double a, double b) {   // lapack.cpp's local hypo
 }
 
 // JacobiSVDImpl_<double>: one-sided Jacobi on the N rows (length M) of At.  On return W = singular values
-// (descending), rows i < N1 of At scaled to unit length (= rows of U^T), Vt (if WANT_V) = V^T.
-// On the device every instance (3x3, 6x3, 6x4, 6x5) is fully unrolled over rows, pairs and columns (only the sweep loop
-// stays a loop; the descending selection sort swaps under a predicate instead of through a computed row index), so
-// At / Vt / W are only ever indexed statically and live in registers rather than in local memory.
+// (descending), rows i < n1 of At scaled to unit length (= rows of U^T), Vt (if not null) = V^T.
+// One compact copy of the code serves every small instance (3x3, 6x3, 6x4, 6x5): sizes are run-time arguments and the
+// matrices live in strided scratch memory (shared memory on the device), because fully unrolled per-size copies made the
+// hypothesis kernel 500 KB of straight-line code that spent 44 % of its stall samples waiting for instruction fetches
+// (profiles/r02d_hyp_*).
 #if defined(__CUDA_ARCH__)
 #define P2P_UNROLL _Pragma("unroll")
+#define P2P_NOINLINE __noinline__
 #else
 #define P2P_UNROLL
+#define P2P_NOINLINE
 #endif
-template <int M, int N, bool WANT_V, int N1, int S = 1>
-P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
+template <int S>
+P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, double* Vt, int n1) {
     const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
 #define P2P_AT(i, k) At[((i) * M + (k)) * S]
-    P2P_UNROLL
+#define P2P_VT(i, k) Vt[((i) * N + (k)) * S]
+#define P2P_W(i) W[(i) * S]
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-        P2P_UNROLL
         for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
-        W[i] = sd;
-        if (WANT_V) {
-            P2P_UNROLL
-            for (int k = 0; k < N; ++k) Vt[i * N + k] = (k == i) ? 1 : 0;
-        }
+        P2P_W(i) = sd;
+        if (Vt)
+            for (int k = 0; k < N; ++k) P2P_VT(i, k) = (k == i) ? 1 : 0;
     }
     const int max_iter = M > 30 ? M : 30;
     for (int iter = 0; iter < max_iter; ++iter) {
         bool changed = false;
-        P2P_UNROLL
-        for (int i = 0; i < N - 1; ++i) {
-            P2P_UNROLL
+        for (int i = 0; i < N - 1; ++i)
             for (int j = i + 1; j < N; ++j) {
-                double a = W[i], p = 0, b = W[j];
-                P2P_UNROLL
+                double a = P2P_W(i), p = 0, b = P2P_W(j);
                 for (int k = 0; k < M; ++k) p += P2P_AT(i, k) * P2P_AT(j, k);
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
@@ -232,7 +230,6 @@ P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
-                P2P_UNROLL
                 for (int k = 0; k < M; ++k) {
                     const double x = P2P_AT(i, k), y = P2P_AT(j, k);
                     const double t0 = c * x + s * y;
@@ -242,88 +239,68 @@ P2P_HD inline void cv_jacobi_svd(double* At, double* W, double* Vt) {
                     a += t0 * t0;
                     b += t1 * t1;
                 }
-                W[i] = a;
-                W[j] = b;
+                P2P_W(i) = a;
+                P2P_W(j) = b;
                 changed = true;
-                if (WANT_V) {
-                    P2P_UNROLL
+                if (Vt)
                     for (int k = 0; k < N; ++k) {
-                        const double x = Vt[i * N + k], y = Vt[j * N + k];
-                        Vt[i * N + k] = c * x + s * y;
-                        Vt[j * N + k] = -s * x + c * y;
+                        const double x = P2P_VT(i, k), y = P2P_VT(j, k);
+                        P2P_VT(i, k) = c * x + s * y;
+                        P2P_VT(j, k) = -s * x + c * y;
                     }
-                }
             }
-        }
         if (!changed) break;
     }
-    P2P_UNROLL
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-        P2P_UNROLL
         for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
-        W[i] = sqrt(sd);
+        P2P_W(i) = sqrt(sd);
     }
-    P2P_UNROLL
     for (int i = 0; i < N - 1; ++i) {   // selection sort, descending: j = first maximum of W[i..]
         int j = i;
-        double wj = W[i];
-        P2P_UNROLL
         for (int k = i + 1; k < N; ++k)
-            if (wj < W[k]) { j = k; wj = W[k]; }
-        P2P_UNROLL
-        for (int jj = i + 1; jj < N; ++jj)
-            if (j == jj) {
-                const double tw = W[i]; W[i] = W[jj]; W[jj] = tw;
-                P2P_UNROLL
-                for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(jj, k); P2P_AT(jj, k) = t; }
-                if (WANT_V) {
-                    P2P_UNROLL
-                    for (int k = 0; k < N; ++k) { const double t = Vt[i * N + k]; Vt[i * N + k] = Vt[jj * N + k]; Vt[jj * N + k] = t; }
-                }
-            }
+            if (P2P_W(j) < P2P_W(k)) j = k;
+        if (i != j) {
+            const double tw = P2P_W(i); P2P_W(i) = P2P_W(j); P2P_W(j) = tw;
+            for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(j, k); P2P_AT(j, k) = t; }
+            if (Vt)
+                for (int k = 0; k < N; ++k) { const double t = P2P_VT(i, k); P2P_VT(i, k) = P2P_VT(j, k); P2P_VT(j, k) = t; }
+        }
     }
     // unit rows; a singular value <= DBL_MIN gets a vector regenerated from the fixed-seed RNG and orthogonalised
     // against the previous rows (exactly rank-deficient input, e.g. coplanar points with one coordinate constant)
     unsigned long long rng = 0x12345678ull;
-    P2P_UNROLL
-    for (int i = 0; i < N1; ++i) {
-        double sd = W[i];
+    for (int i = 0; i < n1; ++i) {
+        double sd = P2P_W(i);
         for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
             const double val0 = 1. / M;
-            P2P_UNROLL
             for (int k = 0; k < M; ++k) {
                 rng = (unsigned long long)(unsigned)rng * 4164903690ull + (unsigned)(rng >> 32);
                 P2P_AT(i, k) = ((unsigned)rng & 256) != 0 ? val0 : -val0;
             }
-            for (int it = 0; it < 2; ++it) {
-                P2P_UNROLL
+            for (int it = 0; it < 2; ++it)
                 for (int j = 0; j < i; ++j) {
                     sd = 0;
-                    P2P_UNROLL
                     for (int k = 0; k < M; ++k) sd += P2P_AT(i, k) * P2P_AT(j, k);
                     double asum = 0;
-                    P2P_UNROLL
                     for (int k = 0; k < M; ++k) {
                         const double t = P2P_AT(i, k) - sd * P2P_AT(j, k);
                         P2P_AT(i, k) = t;
                         asum += fabs(t);
                     }
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    P2P_UNROLL
                     for (int k = 0; k < M; ++k) P2P_AT(i, k) *= asum;
                 }
-            }
             sd = 0;
-            P2P_UNROLL
             for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
             sd = sqrt(sd);
         }
         const double sc = sd > minval ? 1 / sd : 0.;
-        P2P_UNROLL
         for (int k = 0; k < M; ++k) P2P_AT(i, k) *= sc;
     }
 #undef P2P_AT
+#undef P2P_VT
+#undef P2P_W
 }
 
 // The same routine specialised for what EPnP asks of the 12 x 12 M^T M (U^T only), laid out for a GPU thread: row i
@@ -430,60 +407,64 @@ P2P_UNROLL
 #undef P2P_AT
 }
 
-// cv::SVD::compute(A, w, u, vt) for a 3x3 A (row-major): ut = U^T (rows = left singular vectors), vt = V^T.
-P2P_HD inline void cv_svd3(const double* A, double* w, double* ut, double* vt) {
+// Scratch convention: every routine below that needs an SVD takes `ws`, >= kWs doubles with element stride S.
+constexpr int kWs = 60;   // 6x5 solve: at 30 + vt 25 + w 5
+
+// cv::SVD::compute(A, w, u, vt) for a 3x3 A (row-major, dense): results in ws -- ut = U^T at [0,9) (rows = left singular
+// vectors), vt = V^T at [9,18), w at [18,21).  want_v = false: cvSVD(A, W, Ut, 0, CV_SVD_U_T).
+template <int S>
+P2P_HD inline void cv_svd3(const double* A, double* ws, bool want_v = true) {
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) ut[i * 3 + j] = A[j * 3 + i];
-    cv_jacobi_svd<3, 3, true, 3>(ut, w, vt);
-}
-// same without V (cvSVD(A, W, Ut, 0, CV_SVD_U_T))
-P2P_HD inline void cv_svd3_ut(const double* A, double* ut, double* w) {
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) ut[i * 3 + j] = A[j * 3 + i];
-    cv_jacobi_svd<3, 3, false, 3>(ut, w, nullptr);
+        for (int j = 0; j < 3; ++j) ws[(i * 3 + j) * S] = A[j * 3 + i];
+    cv_jacobi_svd<S>(ws, 3, 3, ws + 18 * S, want_v ? ws + 9 * S : nullptr, 3);
 }
 
 // cvInvert(A, Ainv, CV_SVD) for 3x3: SVD::compute + SVD::backSubst (SVBkSbImpl_ with an identity right-hand side).
-P2P_HD inline void cv_invert3_svd(const double* A, double* x) {
-    double w[3], ut[9], vt[9];
-    cv_svd3(A, w, ut, vt);
+template <int S>
+P2P_HD inline void cv_invert3_svd(const double* A, double* x, double* ws) {
+    cv_svd3<S>(A, ws);
+    const double* ut = ws;
+    const double* vt = ws + 9 * S;
+    const double* w = ws + 18 * S;
     for (int i = 0; i < 9; ++i) x[i] = 0;
     double thr = 0;
-    for (int i = 0; i < 3; ++i) thr += w[i];
+    for (int i = 0; i < 3; ++i) thr += w[i * S];
     thr *= 2.220446049250313e-16 * 2;
     for (int i = 0; i < 3; ++i) {
-        double wi = w[i];
+        double wi = w[i * S];
         if (fabs(wi) <= thr) continue;
         wi = 1 / wi;
         double buf[3];
-        for (int j = 0; j < 3; ++j) buf[j] = ut[i * 3 + j] * wi;
+        for (int j = 0; j < 3; ++j) buf[j] = ut[(i * 3 + j) * S] * wi;
         for (int r = 0; r < 3; ++r) {
-            const double s = vt[i * 3 + r];
-            for (int j = 0; j < 3; ++j) x[r * 3 + j] = x[r * 3 + j] + s * buf[j];
+            const double sv = vt[(i * 3 + r) * S];
+            for (int j = 0; j < 3; ++j) x[r * 3 + j] = x[r * 3 + j] + sv * buf[j];
         }
     }
 }
 
-// cvSolve(A, b, x, CV_SVD) for a 6 x N system (N <= 5): minimum-norm least squares, singular values
-// <= 2*DBL_EPSILON*sum(w) dropped.
-template <int N>
-P2P_HD inline void cv_solve6_svd(const double* A, const double* b, double* x) {
-    double at[N * 6], w[N], vt[N * N];
+// cvSolve(A, b, x, CV_SVD) for the 6 x N system (N <= 5) whose column c is column cols[c] of the 6 x 10 matrix `l`
+// (element stride S): minimum-norm least squares, singular values <= 2*DBL_EPSILON*sum(w) dropped.
+template <int S>
+P2P_HD inline void cv_solve6_svd(const double* l, const int* cols, int N, const double* b, double* x, double* ws) {
+    double* at = ws;
+    double* vt = ws + 6 * N * S;
+    double* w = vt + N * N * S;
     for (int i = 0; i < N; ++i)
-        for (int j = 0; j < 6; ++j) at[i * 6 + j] = A[j * N + i];
-    cv_jacobi_svd<6, N, true, N>(at, w, vt);
+        for (int j = 0; j < 6; ++j) at[(i * 6 + j) * S] = l[(j * 10 + cols[i]) * S];
+    cv_jacobi_svd<S>(at, 6, N, w, vt, N);
     for (int i = 0; i < N; ++i) x[i] = 0;
     double thr = 0;
-    for (int i = 0; i < N; ++i) thr += w[i];
+    for (int i = 0; i < N; ++i) thr += w[i * S];
     thr *= 2.220446049250313e-16 * 2;
     for (int i = 0; i < N; ++i) {
-        double wi = w[i];
+        double wi = w[i * S];
         if (fabs(wi) <= thr) continue;
         wi = 1 / wi;
-        double s = 0;
-        for (int j = 0; j < 6; ++j) s += at[i * 6 + j] * b[j];
-        s *= wi;
-        for (int j = 0; j < N; ++j) x[j] = x[j] + s * vt[i * N + j];
+        double sum = 0;
+        for (int j = 0; j < 6; ++j) sum += at[(i * 6 + j) * S] * b[j];
+        sum *= wi;
+        for (int j = 0; j < N; ++j) x[j] = x[j] + sum * vt[(i * N + j) * S];
     }
 }
 
@@ -531,22 +512,23 @@ P2P_HD inline bool qr_solve_6x4(double* A, double* b, double* x) {
 
 // ---- control points (epnp.cpp choose_control_points) from the centroid and the 3x3 scatter
 // PW0^T PW0 of the n reference points.
-P2P_HD inline void choose_control_points(const double* centroid, const double* scatter, int n, double cws[4][3]) {
-    double Ut[9], w[3];
-    cv_svd3_ut(scatter, Ut, w);
+template <int S>
+P2P_HD inline void choose_control_points(const double* centroid, const double* scatter, int n, double cws[4][3], double* ws) {
+    cv_svd3<S>(scatter, ws, false);
     for (int j = 0; j < 3; ++j) cws[0][j] = centroid[j];
     for (int i = 1; i < 4; ++i) {
-        const double k = sqrt(w[i - 1] / n);
-        for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * Ut[3 * (i - 1) + j];
+        const double k = sqrt(ws[(18 + i - 1) * S] / n);
+        for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * ws[(3 * (i - 1) + j) * S];
     }
 }
 
 // cc_inv of compute_barycentric_coordinates: cvInvert(CC, CC_inv, CV_SVD) of [c1-c0 c2-c0 c3-c0].
-P2P_HD inline void control_inverse(const double cws[4][3], double* ci) {
+template <int S>
+P2P_HD inline void control_inverse(const double cws[4][3], double* ci, double* ws) {
     double cc[9];
     for (int i = 0; i < 3; ++i)
         for (int j = 1; j < 4; ++j) cc[3 * i + j - 1] = cws[j][i] - cws[0][i];
-    cv_invert3_svd(cc, ci);
+    cv_invert3_svd<S>(cc, ci, ws);
 }
 
 P2P_HD inline void barycentric(const double* ci, const double cws[4][3], const double* p, double* a) {
@@ -563,32 +545,29 @@ P2P_HD inline void m_rows(const double* a, double u, double v, const Cam& cam, d
     }
 }
 
-// ut8 = rows 8..11 of the 12 x 12 eigenvector matrix (4 x 12): the null-space candidates, smallest eigenvalue last
+// ut8 = rows 8..11 of the 12 x 12 eigenvector matrix (4 x 12): the null-space candidates, smallest eigenvalue last.
+// `l` (6 x 10, element stride S) receives L_6x10.
+template <int S>
 P2P_HD inline void compute_L_6x10(const double* ut8, double* l) {
     const double* v[4] = {ut8 + 12 * 3, ut8 + 12 * 2, ut8 + 12 * 1, ut8};
-    double dv[4][6][3];
-    for (int i = 0; i < 4; ++i) {
-        int a = 0, b = 1;
-        for (int j = 0; j < 6; ++j) {
-            dv[i][j][0] = v[i][3 * a] - v[i][3 * b];
-            dv[i][j][1] = v[i][3 * a + 1] - v[i][3 * b + 1];
-            dv[i][j][2] = v[i][3 * a + 2] - v[i][3 * b + 2];
-            ++b;
-            if (b > 3) { ++a; b = a + 1; }
-        }
-    }
+    int a = 0, b = 1;
     for (int i = 0; i < 6; ++i) {
-        double* r = l + 10 * i;
-        r[0] = dot3(dv[0][i], dv[0][i]);
-        r[1] = 2.0 * dot3(dv[0][i], dv[1][i]);
-        r[2] = dot3(dv[1][i], dv[1][i]);
-        r[3] = 2.0 * dot3(dv[0][i], dv[2][i]);
-        r[4] = 2.0 * dot3(dv[1][i], dv[2][i]);
-        r[5] = dot3(dv[2][i], dv[2][i]);
-        r[6] = 2.0 * dot3(dv[0][i], dv[3][i]);
-        r[7] = 2.0 * dot3(dv[1][i], dv[3][i]);
-        r[8] = 2.0 * dot3(dv[2][i], dv[3][i]);
-        r[9] = dot3(dv[3][i], dv[3][i]);
+        double dv[4][3];
+        for (int q = 0; q < 4; ++q)
+            for (int c = 0; c < 3; ++c) dv[q][c] = v[q][3 * a + c] - v[q][3 * b + c];
+        double* r = l + 10 * i * S;
+        r[0 * S] = dot3(dv[0], dv[0]);
+        r[1 * S] = 2.0 * dot3(dv[0], dv[1]);
+        r[2 * S] = dot3(dv[1], dv[1]);
+        r[3 * S] = 2.0 * dot3(dv[0], dv[2]);
+        r[4 * S] = 2.0 * dot3(dv[1], dv[2]);
+        r[5 * S] = dot3(dv[2], dv[2]);
+        r[6 * S] = 2.0 * dot3(dv[0], dv[3]);
+        r[7 * S] = 2.0 * dot3(dv[1], dv[3]);
+        r[8 * S] = 2.0 * dot3(dv[2], dv[3]);
+        r[9 * S] = dot3(dv[3], dv[3]);
+        ++b;
+        if (b > 3) { ++a; b = a + 1; }
     }
 }
 
@@ -598,27 +577,29 @@ P2P_HD inline void compute_rho(const double cws[4][3], double* rho) {
 }
 
 // betas10 = [B11 B12 B22 B13 B23 B33 B14 B24 B34 B44]
-P2P_HD inline void find_betas_approx_1(const double* l, const double* rho, double* betas) {  // [B11 B12 B13 B14]
-    double L[24], b4[4];
-    for (int i = 0; i < 6; ++i) { L[i * 4] = l[i * 10]; L[i * 4 + 1] = l[i * 10 + 1]; L[i * 4 + 2] = l[i * 10 + 3]; L[i * 4 + 3] = l[i * 10 + 6]; }
-    cv_solve6_svd<4>(L, rho, b4);
+template <int S>
+P2P_HD inline void find_betas_approx_1(const double* l, const double* rho, double* betas, double* ws) {  // [B11 B12 B13 B14]
+    const int cols[4] = {0, 1, 3, 6};
+    double b4[4];
+    cv_solve6_svd<S>(l, cols, 4, rho, b4, ws);
     if (b4[0] < 0) { betas[0] = sqrt(-b4[0]); betas[1] = -b4[1] / betas[0]; betas[2] = -b4[2] / betas[0]; betas[3] = -b4[3] / betas[0]; }
     else { betas[0] = sqrt(b4[0]); betas[1] = b4[1] / betas[0]; betas[2] = b4[2] / betas[0]; betas[3] = b4[3] / betas[0]; }
 }
-P2P_HD inline void find_betas_approx_2(const double* l, const double* rho, double* betas) {  // [B11 B12 B22]
-    double L[18], b3[3];
-    for (int i = 0; i < 6; ++i) { L[i * 3] = l[i * 10]; L[i * 3 + 1] = l[i * 10 + 1]; L[i * 3 + 2] = l[i * 10 + 2]; }
-    cv_solve6_svd<3>(L, rho, b3);
+template <int S>
+P2P_HD inline void find_betas_approx_2(const double* l, const double* rho, double* betas, double* ws) {  // [B11 B12 B22]
+    const int cols[3] = {0, 1, 2};
+    double b3[3];
+    cv_solve6_svd<S>(l, cols, 3, rho, b3, ws);
     if (b3[0] < 0) { betas[0] = sqrt(-b3[0]); betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
     else { betas[0] = sqrt(b3[0]); betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
     if (b3[1] < 0) betas[0] = -betas[0];
     betas[2] = 0.0; betas[3] = 0.0;
 }
-P2P_HD inline void find_betas_approx_3(const double* l, const double* rho, double* betas) {  // [B11 B12 B22 B13 B23]
-    double L[30], b5[5];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 5; ++j) L[i * 5 + j] = l[i * 10 + j];
-    cv_solve6_svd<5>(L, rho, b5);
+template <int S>
+P2P_HD inline void find_betas_approx_3(const double* l, const double* rho, double* betas, double* ws) {  // [B11 B12 B22 B13 B23]
+    const int cols[5] = {0, 1, 2, 3, 4};
+    double b5[5];
+    cv_solve6_svd<S>(l, cols, 5, rho, b5, ws);
     if (b5[0] < 0) { betas[0] = sqrt(-b5[0]); betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
     else { betas[0] = sqrt(b5[0]); betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
     if (b5[1] < 0) betas[0] = -betas[0];
@@ -626,12 +607,14 @@ P2P_HD inline void find_betas_approx_3(const double* l, const double* rho, doubl
     betas[3] = 0.0;
 }
 
-P2P_HD inline void gauss_newton(const double* l, const double* rho, double* betas) {
+template <int S>
+P2P_HD P2P_NOINLINE void gauss_newton(const double* l, const double* rho, double* betas) {
     double x[4] = {0, 0, 0, 0};
     for (int it = 0; it < 5; ++it) {
         double A[24], b[6];
         for (int i = 0; i < 6; ++i) {
-            const double* r = l + i * 10;
+            double r[10];
+            for (int c = 0; c < 10; ++c) r[c] = l[(i * 10 + c) * S];
             A[i * 4 + 0] = 2 * r[0] * betas[0] + r[1] * betas[1] + r[3] * betas[2] + r[6] * betas[3];
             A[i * 4 + 1] = r[1] * betas[0] + 2 * r[2] * betas[1] + r[4] * betas[2] + r[7] * betas[3];
             A[i * 4 + 2] = r[3] * betas[0] + r[4] * betas[1] + 2 * r[5] * betas[2] + r[8] * betas[3];
@@ -647,32 +630,35 @@ P2P_HD inline void gauss_newton(const double* l, const double* rho, double* beta
 }
 
 // The three refined beta sets from the four null-space candidates ut8 (rows 8..11 of U^T) -- epnp.cpp compute_pose,
-// middle part.
-P2P_HD inline void betas_from_ut(const double* ut8, const double cws[4][3], double betas[3][4]) {
-    double l[60], rho[6];
-    compute_L_6x10(ut8, l);
+// middle part.  `lws`: scratch of 60 + kWs doubles (element stride S): L_6x10, then the SVD workspace.
+template <int S>
+P2P_HD inline void betas_from_ut(const double* ut8, const double cws[4][3], double betas[3][4], double* lws) {
+    double rho[6];
+    double* l = lws;
+    double* ws = lws + 60 * S;
+    compute_L_6x10<S>(ut8, l);
     compute_rho(cws, rho);
-    find_betas_approx_1(l, rho, betas[0]); gauss_newton(l, rho, betas[0]);
-    find_betas_approx_2(l, rho, betas[1]); gauss_newton(l, rho, betas[1]);
-    find_betas_approx_3(l, rho, betas[2]); gauss_newton(l, rho, betas[2]);
+    find_betas_approx_1<S>(l, rho, betas[0], ws); gauss_newton<S>(l, rho, betas[0]);
+    find_betas_approx_2<S>(l, rho, betas[1], ws); gauss_newton<S>(l, rho, betas[1]);
+    find_betas_approx_3<S>(l, rho, betas[2], ws); gauss_newton<S>(l, rho, betas[2]);
 }
 
 // Large-n refit path: the eigenvectors of the four smallest eigenvalues of M^T M by tridiagonal QL (for n >= 6 noisy
 // points they are well separated, so any accurate eigen-solver agrees with cv2 to ~1e-13; signs cancel in the betas).
 P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
-    double w[12];
+    double w[12], lws[60 + kWs];
     tridiag_eig_sym<12, 8>(mtm, ut8, w);
-    betas_from_ut(ut8, cws, betas);
+    betas_from_ut<1>(ut8, cws, betas, lws);
 }
 
-// Small-n path, bit-exact: cvSVD(MtM, D, Ut, 0, CV_SVD_MODIFY_A | CV_SVD_U_T) in place on `mtm` (element stride S),
-// rows 8..11 copied out.
+// Small-n path, bit-exact: cvSVD(MtM, D, Ut, 0, CV_SVD_MODIFY_A | CV_SVD_U_T) in place on `mtm` (144 doubles, element
+// stride S); rows 8..11 are copied out and the storage is then reused as the L_6x10 / SVD scratch.
 template <int S = 1>
 P2P_HD inline void solve_betas_exact(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
     double w[12];
     cv_jacobi_svd12_ut<S>(mtm, w);   // MtM is bitwise symmetric, so A^T = A
     for (int i = 0; i < 48; ++i) ut8[i] = mtm[(96 + i) * S];
-    betas_from_ut(ut8, cws, betas);
+    betas_from_ut<S>(ut8, cws, betas, mtm);
 }
 
 // cvMulTransposed(M, MtM, 1) for the 2n x 12 matrix fill_M builds, restated on its sparsity: per entry the same
@@ -722,12 +708,13 @@ P2P_HD inline void camera_point(const double* a, const double ccs[4][3], double*
 
 // estimate_R_and_t from the centroids and the 3x3 correlation ABt = sum (pc-pc0)(pw-pw0)^T:
 // cvSVD(ABt, D, U, V, CV_SVD_MODIFY_A), R = U V^T with the det < 0 fix on the last row.
-P2P_HD inline void rt_from_correlation(const double* abt, const double* pc0, const double* pw0, double R[3][3], double* t) {
-    double w[3], ut[9], vt[9];
-    cv_svd3(abt, w, ut, vt);
+template <int S>
+P2P_HD inline void rt_from_correlation(const double* abt, const double* pc0, const double* pw0, double R[3][3], double* t, double* ws) {
+    cv_svd3<S>(abt, ws);
     // U[i][k] = ut[k][i], V[j][k] = vt[k][j]
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[i][j] = ut[i] * vt[j] + ut[3 + i] * vt[3 + j] + ut[6 + i] * vt[6 + j];
+        for (int j = 0; j < 3; ++j)
+            R[i][j] = ws[i * S] * ws[(9 + j) * S] + ws[(3 + i) * S] * ws[(12 + j) * S] + ws[(6 + i) * S] * ws[(15 + j) * S];
     const double det = R[0][0] * R[1][1] * R[2][2] + R[0][1] * R[1][2] * R[2][0] + R[0][2] * R[1][0] * R[2][1] -
                        R[0][2] * R[1][1] * R[2][0] - R[0][1] * R[1][0] * R[2][2] - R[0][0] * R[1][2] * R[2][1];
     if (det < 0) { R[2][0] = -R[2][0]; R[2][1] = -R[2][1]; R[2][2] = -R[2][2]; }
@@ -743,13 +730,15 @@ P2P_HD inline double reproj_dist(const double R[3][3], const double* t, const do
 }
 
 // cv::Rodrigues, matrix -> vector (after projecting R onto SO(3) through its SVD) and back.
-P2P_HD inline void rodrigues_to_vec(const double Rin[3][3], double* r) {
-    double A[9], w[3], ut[9], vt[9], R[9];
+template <int S>
+P2P_HD inline void rodrigues_to_vec(const double Rin[3][3], double* r, double* ws) {
+    double A[9], R[9];
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) A[i * 3 + j] = Rin[i][j];
-    cv_svd3(A, w, ut, vt);   // SVD::compute(R, W, U, Vt); R = U*Vt
+    cv_svd3<S>(A, ws);   // SVD::compute(R, W, U, Vt); R = U*Vt
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[i * 3 + j] = ut[i] * vt[j] + ut[3 + i] * vt[3 + j] + ut[6 + i] * vt[6 + j];
+        for (int j = 0; j < 3; ++j)
+            R[i * 3 + j] = ws[i * S] * ws[(9 + j) * S] + ws[(3 + i) * S] * ws[(12 + j) * S] + ws[(6 + i) * S] * ws[(15 + j) * S];
     double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
     const double sn = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
     double c = (R[0] + R[4] + R[8] - 1) * 0.5;
@@ -837,7 +826,8 @@ P2P_HD inline void refit_candidates(const double* s, int m, const double* c0, co
                 for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s[40 + j * 3 + q];
         for (int r = 0; r < 3; ++r)
             for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * dsum[q];
-        rt_from_correlation(abt, pc0, c0, Rs[c], ts[c]);
+        double ws[kWs];
+        rt_from_correlation<1>(abt, pc0, c0, Rs[c], ts[c], ws);
     }
 }
 
@@ -856,9 +846,9 @@ P2P_HD inline void solve_small(const double* pws, const double* us, int n, const
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) sc[a * 3 + b] += d[a] * d[b];
     }
-    choose_control_points(c0, sc, n, cws);
+    choose_control_points<S>(c0, sc, n, cws, mtm);   // `mtm` doubles as the SVD scratch until M^T M is built
     double ci[9], alphas[MAXN * 4];
-    control_inverse(cws, ci);
+    control_inverse<S>(cws, ci, mtm);
     for (int i = 0; i < n; ++i) barycentric(ci, cws, pws + 3 * i, alphas + 4 * i);
     mtm_exact<S>(alphas, us, n, cam, mtm);
     double ut[48], betas[3][4];   // rows 8..11 of U^T only
@@ -878,7 +868,7 @@ P2P_HD inline void solve_small(const double* pws, const double* us, int n, const
             for (int j = 0; j < 3; ++j)
                 for (int m = 0; m < 3; ++m) abt[3 * j + m] += (pcs[3 * i + j] - pc0[j]) * (pws[3 * i + m] - pw0[m]);
         double Rk[3][3], tk[3];
-        rt_from_correlation(abt, pc0, pw0, Rk, tk);
+        rt_from_correlation<S>(abt, pc0, pw0, Rk, tk, mtm + 60 * S);
         double err = 0;
         for (int i = 0; i < n; ++i) err += reproj_dist(Rk, tk, pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
         err /= n;

@@ -578,7 +578,8 @@ Pipeline::Pipeline(Engine* eng, int max_dets_, int n_th_) : engine(eng), max_det
 }
 Pipeline::~Pipeline() {
     for (auto& g : graphs_)
-        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        for (auto& e : g.second.exec)
+            if (e) cudaGraphExecDestroy(e);
     if (pinned_dets_) cudaFreeHost(pinned_dets_);
     if (pinned_recs_) cudaFreeHost(pinned_recs_);
     for (auto e : fwd_ev_) cudaEventDestroy(e);
@@ -599,77 +600,71 @@ void Pipeline::ensure_pool(long long px) {
 
 // The kernels of one run, in stream order.  Nothing here depends on values the host does not already have: live counts
 // stay on the device (n_active_, CandStats::det), so the sequence can be captured into a CUDA graph.
-void Pipeline::enqueue(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H,
-                       int W, int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s) {
+// phase 0: stage-1 crops | 1: stage-1 forwards | 2: stage-1 post, candidate scan, stage-2 crops | 3: stage-2 forwards |
+// 4: stage-2 post, EPnP-RANSAC, selection.  (Five graphs per configuration rather than one, so that run() can put real
+// timing events around the generator forwards: events recorded by graph nodes cannot be used with cudaEventElapsedTime.)
+void Pipeline::enqueue(int phase, const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32,
+                       int H, int W, int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s) {
     const int cap = engine->cap;
     const int C = n * n_th;
     const uint8_t* fr_u8 = static_cast<const uint8_t*>(frames_dev);
     const float* fr_f32 = static_cast<const float*>(frames_dev);
-    // stage 1
-    if (frames_f32) crop_resize_kernel<false, float><<<dim3(n, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
-    else crop_resize_kernel<false, uint8_t><<<dim3(n, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
-    P2P_CUDA(cudaGetLastError());
-    // The generator forwards are bracketed by event-record nodes (they are part of the captured graph): after a run,
-    // forward_ms() is the device time the tcgen05 generator spent in it -- bench.py's live roofline numerator.
-    n_fwd_ev_ = 0;
-    auto fwd_mark = [&]() {
-        if (n_fwd_ev_ == static_cast<int>(fwd_ev_.size())) {
-            cudaEvent_t e;
-            P2P_CUDA(cudaEventCreate(&e));
-            fwd_ev_.push_back(e);
+    (void)fr_u8; (void)fr_f32;
+    if (phase == 0) {
+        if (frames_f32) crop_resize_kernel<false, float><<<dim3(n, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
+        else crop_resize_kernel<false, uint8_t><<<dim3(n, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, nullptr, nullptr, n_th, x1_.p);
+        P2P_CUDA(cudaGetLastError());
+        launches += 1;
+    } else if (phase == 1) {
+        for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg)
+            for (int b = 0; b < seg_counts[sg]; b += cap) {
+                const int nb = std::min(cap, seg_counts[sg] - b);
+                const size_t at = static_cast<size_t>(d0 + b);
+                engine->forward(*models[sg], x1_.p + at * 16384 * 3, nb, dec1_.p + at * 16384 * 3, prob1_.p + at * 16384, nullptr, s);
+            }
+    } else if (phase == 2) {
+        if (!ov_dec_[0].empty()) {   // parity hook (never inside a captured graph)
+            P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+            P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+            P2P_CUDA(cudaStreamSynchronize(s));
+            ov_dec_[0].clear(); ov_prob_[0].clear();
         }
-        P2P_CUDA(cudaEventRecord(fwd_ev_[n_fwd_ev_++], s));
-    };
-    fwd_mark();
-    for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg)
-        for (int b = 0; b < seg_counts[sg]; b += cap) {
-            const int nb = std::min(cap, seg_counts[sg] - b);
-            const size_t at = static_cast<size_t>(d0 + b);
-            engine->forward(*models[sg], x1_.p + at * 16384 * 3, nb, dec1_.p + at * 16384 * 3, prob1_.p + at * 16384, nullptr, s);
+        stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, n_th, H, W, box_size);
+        P2P_CUDA(cudaGetLastError());
+        P2P_CUDA(cudaMemsetAsync(cands_.p, 0xff, sizeof(CandStats) * C, s));    // det = -1: slot not (yet) a live candidate
+        cand_scan_kernel<<<n_seg, 256, 0, s>>>(state_.p, cands_.p, seg_tab_.p, n_seg, n_th, n_active_.p, cap);
+        P2P_CUDA(cudaGetLastError());
+        if (frames_f32) crop_resize_kernel<true, float><<<dim3(C, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
+        else crop_resize_kernel<true, uint8_t><<<dim3(C, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
+        P2P_CUDA(cudaGetLastError());
+        launches += 3;
+    } else if (phase == 3) {
+        for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg) {
+            const int Cs = seg_counts[sg] * n_th;
+            const int c0 = host_seg_[n_seg + 1 + sg];
+            for (int j = 0; j * cap < Cs; ++j) {
+                const int nb = std::min(cap, Cs - j * cap);
+                const size_t at = static_cast<size_t>(d0) * n_th + static_cast<size_t>(j) * cap;
+                engine->forward(*models[sg], x2_.p + at * 16384 * 3, nb, dec2_.p + at * 16384 * 3, prob2_.p + at * 16384,
+                                n_active_.p + c0 + j, s);
+            }
         }
-    fwd_mark();
-    if (!ov_dec_[0].empty()) {   // parity hook (never inside a captured graph)
-        P2P_CUDA(cudaMemcpyAsync(dec1_.p, ov_dec_[0].data(), std::min(ov_dec_[0].size(), dec1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaMemcpyAsync(prob1_.p, ov_prob_[0].data(), std::min(ov_prob_[0].size(), prob1_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaStreamSynchronize(s));
-        ov_dec_[0].clear(); ov_prob_[0].clear();
-    }
-    stage1_post_kernel<<<n, 256, 0, s>>>(dets_.p, state_.p, dec1_.p, prob1_.p, bits1_.p, n_th, H, W, box_size);
-    P2P_CUDA(cudaGetLastError());
-    P2P_CUDA(cudaMemsetAsync(cands_.p, 0xff, sizeof(CandStats) * C, s));    // det = -1: slot not (yet) a live candidate
-    cand_scan_kernel<<<n_seg, 256, 0, s>>>(state_.p, cands_.p, seg_tab_.p, n_seg, n_th, n_active_.p, cap);
-    P2P_CUDA(cudaGetLastError());
-    // stage 2
-    if (frames_f32) crop_resize_kernel<true, float><<<dim3(C, 64), 256, 0, s>>>(fr_f32, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
-    else crop_resize_kernel<true, uint8_t><<<dim3(C, 64), 256, 0, s>>>(fr_u8, H, W, dets_.p, state_.p, bits1_.p, n_th, x2_.p);
-    P2P_CUDA(cudaGetLastError());
-    fwd_mark();
-    for (int sg = 0, d0 = 0; sg < n_seg; d0 += seg_counts[sg], ++sg) {
-        const int Cs = seg_counts[sg] * n_th;
-        const int c0 = host_seg_[n_seg + 1 + sg];
-        for (int j = 0; j * cap < Cs; ++j) {
-            const int nb = std::min(cap, Cs - j * cap);
-            const size_t at = static_cast<size_t>(d0) * n_th + static_cast<size_t>(j) * cap;
-            engine->forward(*models[sg], x2_.p + at * 16384 * 3, nb, dec2_.p + at * 16384 * 3, prob2_.p + at * 16384,
-                            n_active_.p + c0 + j, s);
+    } else {
+        if (!ov_dec_[1].empty()) {
+            P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+            P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
+            P2P_CUDA(cudaStreamSynchronize(s));
+            ov_dec_[1].clear(); ov_prob_[1].clear();
         }
+        P2P_CUDA(cudaMemsetAsync(problems_.p, 0, sizeof(PnpProblem) * C, s));  // dead slots: n = 0 -> skipped by the PnP kernels
+        stage2_post_kernel<<<C, kPostThreads, 0, s>>>(dets_.p, state_.p, cands_.p, dec2_.p, prob2_.p, n_th, xyz_u8_.p, valid_.p, obj_.p,
+                                                      img_.p, problems_.p);
+        P2P_CUDA(cudaGetLastError());
+        pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s, max_cap);
+        select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
+        P2P_CUDA(cudaGetLastError());
+        launches += 2;
     }
-    fwd_mark();
-    if (!ov_dec_[1].empty()) {
-        P2P_CUDA(cudaMemcpyAsync(dec2_.p, ov_dec_[1].data(), std::min(ov_dec_[1].size(), dec2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaMemcpyAsync(prob2_.p, ov_prob_[1].data(), std::min(ov_prob_[1].size(), prob2_.n) * sizeof(float), cudaMemcpyHostToDevice, s));
-        P2P_CUDA(cudaStreamSynchronize(s));
-        ov_dec_[1].clear(); ov_prob_[1].clear();
-    }
-    P2P_CUDA(cudaMemsetAsync(problems_.p, 0, sizeof(PnpProblem) * C, s));  // dead slots: n = 0 -> skipped by the PnP kernels
-    stage2_post_kernel<<<C, kPostThreads, 0, s>>>(dets_.p, state_.p, cands_.p, dec2_.p, prob2_.p, n_th, xyz_u8_.p, valid_.p, obj_.p,
-                                                  img_.p, problems_.p);
-    P2P_CUDA(cudaGetLastError());
-    launches += 5;
-    pnp.solve_batch(problems_.p, C, obj_.p, img_.p, pnp_mask_.p, pnp_res_.p, reproj_err, iters, confidence, s, max_cap);
-    select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, pnp_res_.p, recs_.p, n);
-    P2P_CUDA(cudaGetLastError());
-    launches += 1;
 }
 
 void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int F, int H,
@@ -723,7 +718,9 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
 
     const bool overrides = !ov_dec_[0].empty() || !ov_dec_[1].empty();
     static const bool prof_pnp = getenv("P2P_PROF_PNP") && atoi(getenv("P2P_PROF_PNP")) != 0;
-    if (use_graph && !overrides && !prof_pnp && !engine->prof) {
+    const bool graphs = use_graph && !overrides && !prof_pnp && !engine->prof;
+    GraphEntry* ge = nullptr;
+    if (graphs) {
         // everything a kernel argument or a grid dimension depends on
         std::vector<long long> key = {n, n_seg, H, W, frames_f32 ? 1 : 0, reinterpret_cast<long long>(frames_dev), iters,
                                       static_cast<long long>(reproj_err * 4096.0), static_cast<long long>(confidence * 1e9),
@@ -735,33 +732,50 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
         auto it = graphs_.find(key);
         if (it == graphs_.end()) {
             if (graphs_.size() >= 32) {   // bounded cache: drop everything rather than track recency
-                for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+                for (auto& g : graphs_)
+                    for (auto& e : g.second.exec) cudaGraphExecDestroy(e);
                 graphs_.clear();
             }
+            GraphEntry fresh;
             const long long l0 = launches + pnp.launches + engine->launches;
-            cudaGraph_t graph = nullptr;
-            P2P_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-            try {
-                enqueue(models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
-            } catch (...) {
-                cudaStreamEndCapture(s, &graph);
-                if (graph) cudaGraphDestroy(graph);
-                throw;
+            for (int ph = 0; ph < 5; ++ph) {
+                cudaGraph_t graph = nullptr;
+                P2P_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+                try {
+                    enqueue(ph, models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
+                } catch (...) {
+                    cudaStreamEndCapture(s, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    for (int q = 0; q < ph; ++q) cudaGraphExecDestroy(fresh.exec[q]);
+                    throw;
+                }
+                P2P_CUDA(cudaStreamEndCapture(s, &graph));
+                cudaError_t err = cudaGraphInstantiate(&fresh.exec[ph], graph, 0);
+                cudaGraphDestroy(graph);
+                if (err != cudaSuccess) {
+                    for (int q = 0; q < ph; ++q) cudaGraphExecDestroy(fresh.exec[q]);
+                    P2P_CUDA(err);
+                }
             }
-            P2P_CUDA(cudaStreamEndCapture(s, &graph));
-            GraphEntry ge;
-            ge.launches = launches + pnp.launches + engine->launches - l0;
-            cudaError_t err = cudaGraphInstantiate(&ge.exec, graph, 0);
-            cudaGraphDestroy(graph);
-            P2P_CUDA(err);
-            it = graphs_.emplace(key, ge).first;
+            fresh.launches = launches + pnp.launches + engine->launches - l0;
+            it = graphs_.emplace(key, fresh).first;
         } else {
             launches += it->second.launches;   // the counters only saw these kernels while they were captured
         }
-        P2P_CUDA(cudaGraphLaunch(it->second.exec, s));
-    } else {
-        // debug / profiling path: kernel by kernel, with the parity hooks that replace the network outputs
-        enqueue(models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
+        ge = &it->second;
+    }
+    if (fwd_ev_.empty()) {
+        fwd_ev_.resize(4);
+        for (auto& e : fwd_ev_) P2P_CUDA(cudaEventCreate(&e));
+    }
+    for (int ph = 0; ph < 5; ++ph) {
+        // real events around the generator forwards (phases 1 and 3): forward_ms() = bench.py's live roofline numerator
+        if (ph == 1) P2P_CUDA(cudaEventRecord(fwd_ev_[0], s));
+        if (ph == 3) P2P_CUDA(cudaEventRecord(fwd_ev_[2], s));
+        if (ge) P2P_CUDA(cudaGraphLaunch(ge->exec[ph], s));
+        else enqueue(ph, models, seg_counts, n_seg, frames_dev, frames_f32, H, W, n, reproj_err, iters, confidence, max_cap, s);
+        if (ph == 1) P2P_CUDA(cudaEventRecord(fwd_ev_[1], s));
+        if (ph == 3) P2P_CUDA(cudaEventRecord(fwd_ev_[3], s));
     }
     if (fslot >= 0) P2P_CUDA(cudaEventRecord(frames_free_[fslot], s));
     last_n_fwd_ev_ = 4;

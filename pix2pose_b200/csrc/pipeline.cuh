@@ -128,16 +128,16 @@ class Pipeline {
     long long pool_px_ = 0;
     std::vector<DetIn> host_dets_;
     // The kernel sequence of a run has no host-dependent control flow (live counts stay on the device), so it is captured
-    // into a CUDA graph per configuration and replayed: ~150 launches cost one graph launch.
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    // into CUDA graphs (one per phase, see enqueue) per configuration and replayed: ~150 launches cost five graph launches.
+    struct GraphEntry { cudaGraphExec_t exec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; long long launches = 0; };
     std::map<std::vector<long long>, GraphEntry> graphs_;
     long long pool_gen_ = 0;
     std::vector<cudaEvent_t> fwd_ev_;
     int n_fwd_ev_ = 0, last_n_fwd_ev_ = 0;
     DetIn* pinned_dets_ = nullptr;
     PoseRecord* pinned_recs_ = nullptr;
-    void enqueue(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H, int W,
-                 int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s);
+    void enqueue(int phase, const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H,
+                 int W, int n, float reproj_err, int iters, double confidence, int max_cap, cudaStream_t s);
 
   public:
     bool use_graph = true;        // P2P_GRAPH=0 launches kernel by kernel

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kHypThreads, 1) ransac_hyp_kernel(const PnpPro
     }
     double R[3][3], t[3], rv[3];
     epnp::solve_small<5, kHypThreads>(pws, us, 5, cam, s_ws + threadIdx.x, R, t);
-    epnp::rodrigues_to_vec(R, rv);   // the RANSAC model is (rvec, tvec) ...
+    epnp::rodrigues_to_vec<kHypThreads>(R, rv, s_ws + threadIdx.x);   // the RANSAC model is (rvec, tvec) ...
     epnp::rodrigues_to_mat(rv, R);   // ... and projectPoints turns rvec back into a matrix
     double* o = hyp + g * 12;
 #pragma unroll
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kSmallThreads) epnp_refit_small_kernel(const P
         us[2 * j + 1] = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
     }
     epnp::solve_small<kSmallRefit, kSmallThreads>(pws, us, m, cam, s_ws + threadIdx.x, Rk, tk);
-    epnp::rodrigues_to_vec(Rk, rv);
+    epnp::rodrigues_to_vec<kSmallThreads>(Rk, rv, s_ws + threadIdx.x);
     epnp::rodrigues_to_mat(rv, Rf);
     for (int i = 0; i < 3; ++i) {
         out->rvec[i] = rv[i];
@@ -324,8 +324,9 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
     if (threadIdx.x == 0) {
         double sc[9];
         for (int i = 0; i < 9; ++i) sc[i] = s_sum[i];
-        epnp::choose_control_points(c0, sc, m, s_cws);
-        epnp::control_inverse(s_cws, s_ci);
+        double ws[epnp::kWs];
+        epnp::choose_control_points<1>(c0, sc, m, s_cws, ws);
+        epnp::control_inverse<1>(s_cws, s_ci, ws);
     }
     __syncthreads();
     // pass C: M^T M in its structured form (10 alpha pairs x {1, uc-u, vc-v, (uc-u)^2+(vc-v)^2}) and
@@ -382,8 +383,8 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         int N = 0;
         if (s_sum[1] < s_sum[0]) N = 1;
         if (s_sum[2] < s_sum[N]) N = 2;
-        double rv[3], Rf[3][3];
-        epnp::rodrigues_to_vec(s_R[N], rv);
+        double rv[3], Rf[3][3], ws[epnp::kWs];
+        epnp::rodrigues_to_vec<1>(s_R[N], rv, ws);
         epnp::rodrigues_to_mat(rv, Rf);
         for (int i = 0; i < 3; ++i) {
             out->rvec[i] = rv[i];

@@ -26,7 +26,8 @@ void host_rodrigues_roundtrip(const double* R9, double* r3, double* R9out) {
     double R[3][3], Ro[3][3];
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R[i][j] = R9[i * 3 + j];
-    epnp::rodrigues_to_vec(R, r3);
+    double ws[epnp::kWs];
+    epnp::rodrigues_to_vec<1>(R, r3, ws);
     epnp::rodrigues_to_mat(r3, Ro);
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R9out[i * 3 + j] = Ro[i][j];
@@ -42,14 +43,24 @@ void host_eig12(const double* A, double* Vt, double* w) {
 void host_cv_svd12(const double* A, double* w, double* ut, double* vt) {   // cv2.SVDecomp(A) of a 12x12
     for (int i = 0; i < 12; ++i)
         for (int j = 0; j < 12; ++j) ut[i * 12 + j] = A[j * 12 + i];
-    epnp::cv_jacobi_svd<12, 12, true, 12>(ut, w, vt);
+    epnp::cv_jacobi_svd<1>(ut, 12, 12, w, vt, 12);
 }
-void host_cv_svd3(const double* A, double* w, double* ut, double* vt) { epnp::cv_svd3(A, w, ut, vt); }
-void host_cv_invert3(const double* A, double* x) { epnp::cv_invert3_svd(A, x); }                     // cv2.invert(A, DECOMP_SVD)
+void host_cv_svd3(const double* A, double* w, double* ut, double* vt) {
+    double ws[epnp::kWs];
+    epnp::cv_svd3<1>(A, ws);
+    for (int i = 0; i < 9; ++i) { ut[i] = ws[i]; vt[i] = ws[9 + i]; }
+    for (int i = 0; i < 3; ++i) w[i] = ws[18 + i];
+}
+void host_cv_invert3(const double* A, double* x) {                                                   // cv2.invert(A, DECOMP_SVD)
+    double ws[epnp::kWs];
+    epnp::cv_invert3_svd<1>(A, x, ws);
+}
 void host_cv_solve6(const double* A, const double* b, int n, double* x) {                           // cv2.solve(A, b, DECOMP_SVD)
-    if (n == 3) epnp::cv_solve6_svd<3>(A, b, x);
-    else if (n == 4) epnp::cv_solve6_svd<4>(A, b, x);
-    else epnp::cv_solve6_svd<5>(A, b, x);
+    double l[60] = {0}, ws[epnp::kWs];
+    const int cols[5] = {0, 1, 2, 3, 4};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < n; ++j) l[i * 10 + j] = A[i * n + j];
+    epnp::cv_solve6_svd<1>(l, cols, n, b, x, ws);
 }
 // cv2.mulTransposed(M, aTa=True) of the 2n x 12 matrix epnp::fill_M builds from (alphas, us)
 void host_mtm(const double* alphas, const double* us, int n, const double* cam4, double* mtm) {
@@ -69,8 +80,9 @@ void host_refit_large(const double* pws, const double* us, int n, const double* 
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) sc[a * 3 + b] += d[a] * d[b];
     }
-    epnp::choose_control_points(c0, sc, n, cws);
-    epnp::control_inverse(cws, ci);
+    double ws[epnp::kWs];
+    epnp::choose_control_points<1>(c0, sc, n, cws, ws);
+    epnp::control_inverse<1>(cws, ci, ws);
     for (int i = 0; i < n; ++i) {
         double a[4];
         epnp::barycentric(ci, cws, pws + 3 * i, a);
@@ -92,7 +104,7 @@ void host_refit_large(const double* pws, const double* us, int n, const double* 
     int N = 0;
     if (err[1] < err[0]) N = 1;
     if (err[2] < err[N]) N = 2;
-    epnp::rodrigues_to_vec(Rs[N], rvec);
+    epnp::rodrigues_to_vec<1>(Rs[N], rvec, ws);
     for (int i = 0; i < 3; ++i) t3[i] = ts[N][i];
 }
 }
@@ -136,7 +148,7 @@ extern "C" int host_ransac(const double* obj64, const double* img64, int n, cons
         }
         double R[3][3], t[3], rv[3], mtm[144];
         epnp::solve_small<5>(pws, us, 5, cam, mtm, R, t);
-        epnp::rodrigues_to_vec(R, rv);
+        epnp::rodrigues_to_vec<1>(R, rv, mtm);
         epnp::rodrigues_to_mat(rv, R);
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) hyp[h * 12 + i * 3 + j] = R[i][j];
@@ -166,6 +178,6 @@ extern "C" int host_ransac(const double* obj64, const double* img64, int n, cons
     }
     double R[3][3], mtm[144];
     epnp::solve_small<20000>(pw.data(), uv.data(), (int)(pw.size() / 3), cam, mtm, R, tvec);   // n-sized scratch on the stack
-    epnp::rodrigues_to_vec(R, rvec);
+    epnp::rodrigues_to_vec<1>(R, rvec, mtm);
     return max_good;
 }
