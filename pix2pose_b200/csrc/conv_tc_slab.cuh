@@ -24,15 +24,20 @@ template <int BN, int NP>
 struct SlabCfg {
     static constexpr int SLAB_W = 8;
     static constexpr int TILE_H = 16;
-    static constexpr int MAX_ROWS = TILE_H + 4;                       // k = 5: two halo rows above and below
-    static constexpr int SLAB_BYTES = NP * SLAB_W * MAX_ROWS * 128;   // 40 KB (fp16x3)
-    static constexpr int SLAB_BUFS = 2;
+    // BN = 16 (the heads: 3 x 3 taps only): one halo row above and below, and a DEEP slab ring -- a slab feeds just 3 taps of
+    // 8 narrow MMAs (~300 cycles), far less than a TMA round trip, so two buffers left the tensor pipe waiting for loads
+    // (heads 360 -> 414 us per 256 crops with 2 buffers).  The wide convs (5 x 5: 25 taps x 8 wide MMAs per slab column) hide
+    // the latency with two.
+    static constexpr int MAX_ROWS = BN < 64 ? TILE_H + 2 : TILE_H + 4;
+    static constexpr int SLAB_BYTES = NP * SLAB_W * MAX_ROWS * 128;   // 40 KB (fp16x3, k <= 5), 36 KB (heads)
+    static constexpr int SLAB_BUFS = BN < 64 ? (NP == 2 ? 5 : 6) : 2;
     static constexpr int B_BYTES = NP * BN * 128;
-    static constexpr int EPI_BYTES = NP * 128 * 128;
+    static constexpr int EPI_BYTES = BN < 64 ? 0 : NP * 128 * 128;    // the heads store fp32 straight from registers
     static constexpr int B_ROOM = 224 * 1024 - SLAB_BUFS * SLAB_BYTES - EPI_BYTES - 2048;
     static constexpr int B_STAGES = B_ROOM / B_BYTES > 6 ? 6 : B_ROOM / B_BYTES;
-    static constexpr int CONST_BYTES = 2 * BN * 4;
+    static constexpr int CONST_BYTES = 2 * (BN < 64 ? 64 : BN) * 4;
     static constexpr int SMEM_BYTES = SLAB_BUFS * SLAB_BYTES + B_STAGES * B_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CONST_BYTES;
+    static_assert(B_STAGES >= 2, "no room for the weight ring");
 };
 
 // slab table entry (p.kit): {map index | (k16 steps << 8), first channel, first packed-weight k-iteration of
@@ -49,7 +54,7 @@ __global__ void __launch_bounds__(64 + kEpiThreads, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_constant__ CUtensorMap mS1,
                     const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO,
                     const __grid_constant__ ConvParams p) {
-    static_assert(BN == 128, "slab tiles are 128 pixels x 128 channels");
+    static_assert(BN == 128 || BN == 64 || BN == 16, "slab tiles are 128 pixels x 128 / 64 channels (k x k convs) or x 16 accumulator columns (the heads)");
     static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
     using SC = SlabCfg<BN, NP>;
     using PC = PersCfg<BN, NP>;

@@ -348,9 +348,21 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
     c.slab = false;
     c.slabs.clear();
     static const bool slab_on = !getenv("P2P_SLAB") || atoi(getenv("P2P_SLAB")) != 0;
-    if (slab_on && c.kind == K_CONV && c.ksize >= 3 && c.ksize <= 5 && c.BN == 128 && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() <= 2 &&
-        c.res_tensor < 0 && c.splitk <= 1) {
+    static const bool slab64 = !getenv("P2P_SLAB64") || atoi(getenv("P2P_SLAB64")) != 0;   // 3x3 64->64 convs of the stage-2 bottlenecks
+    if (slab_on && c.kind == K_CONV && c.ksize >= 3 && c.ksize <= 5 && (c.BN == 128 || (c.BN == 64 && slab64 && c.Cout == 64)) && c.W % 8 == 0 &&
+        c.H % 16 == 0 && c.srcs.size() <= 2 && c.res_tensor < 0 && c.splitk <= 1) {
         c.slab = true;
+        c.slab_ks = c.ksize;
+    }
+    // The heads (phase-fused transposed conv, N = 16) are a 3 x 3 stride-1 conv over d3_uni from the GEMM's point of view and
+    // were bound by re-fetching the 128-pixel activation tile for each of the 9 taps (9 x 537 MB through L2 per 256 crops for
+    // 1 % of the FLOPs); on the slab kernel a tile's activations arrive 3 x instead of 9 x.
+    static const bool slab_heads = !getenv("P2P_SLAB_HEADS") || atoi(getenv("P2P_SLAB_HEADS")) != 0;
+    if (slab_on && slab_heads && c.kind == K_CONVT_FUSED && c.act == ACT_HEADS && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() == 1) {
+        c.slab = true;
+        c.slab_ks = 3;
+    }
+    if (c.slab) {
         c.tw = 8; c.th = 16; c.nb = 1;
         int src_base = 0;
         for (size_t si = 0; si < c.srcs.size(); ++si) {
@@ -360,7 +372,7 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
                 const int nvalid = std::min(64, sp.c_count - ch * 64);
                 c.slabs.push_back(make_int4(static_cast<int>(si) | (((nvalid + 15) / 16) << 8), sp.c_begin + ch * 64, src_base + ch, nch));
             }
-            src_base += c.ksize * c.ksize * nch;
+            src_base += c.slab_ks * c.slab_ks * nch;
         }
     }
 }
@@ -600,7 +612,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
         memset(rt.mapSlab, 0, sizeof(rt.mapSlab));
         if (c.slab) {
             rt.slabs.upload(c.slabs.data(), c.slabs.size());
-            const int pad = (c.ksize - 1) / 2;
+            const int pad = (c.slab_ks - 1) / 2;
             for (size_t si = 0; si < c.srcs.size(); ++si) {
                 const SrcSpec& sp = c.srcs[si];
                 const TensorSpec& t = plan.tensors[sp.tensor];
@@ -964,17 +976,31 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
             static const int pair_min_bn = getenv("P2P_PAIR_BN128") && atoi(getenv("P2P_PAIR_BN128")) ? 128 : 256;
             const bool use_pair = pair && c.BN >= pair_min_bn && c.splitk <= 1 && c.kind != K_DENSE && c.act != ACT_HEADS &&
                                   c.res_tensor < 0 && rt.has_out && tma_store && grid.x >= 2;
-            if (slab && c.slab && rt.has_out && tma_store) {
-                p.tma_store = 1;
+            if (slab && c.slab && c.act == ACT_HEADS) {
+                p.tma_store = 0;
                 p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
-                p.slab_ksize = c.ksize;
+                p.slab_ksize = c.slab_ks;
                 p.kit = rt.slabs.p;
                 p.kstart[0] = 0;
                 for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
                 for (size_t i = 0; i < c.slabs.size(); ++i) p.ksteps_tab[i] = static_cast<uint8_t>(c.slabs[i].x >> 8);
                 const int tiles = static_cast<int>(grid.x * grid.y);
-                const int cl = tiles >= 2 * num_sms ? slab_cluster : 1;  // small launches: no point in pairing up CTAs
-                if (np == 2) {
+                if (np == 2) launch_conv_slab<16, 2, 1>(rt.mapSlab, mc.mapB, rt.mapSlab[0], p, tiles, num_sms, s);   // (no output map: fp32 stores)
+                else launch_conv_slab<16, 1, 1>(rt.mapSlab, mc.mapB, rt.mapSlab[0], p, tiles, num_sms, s);
+            } else if (slab && c.slab && rt.has_out && tma_store) {
+                p.tma_store = 1;
+                p.nst = 0; p.epi_bufs = 1; p.res_tma = 0;
+                p.slab_ksize = c.slab_ks;
+                p.kit = rt.slabs.p;
+                p.kstart[0] = 0;
+                for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
+                for (size_t i = 0; i < c.slabs.size(); ++i) p.ksteps_tab[i] = static_cast<uint8_t>(c.slabs[i].x >> 8);
+                const int tiles = static_cast<int>(grid.x * grid.y);
+                const int cl = (tiles >= 2 * num_sms && c.BN == 128) ? slab_cluster : 1;  // small launches: no point in pairing up CTAs
+                if (c.BN == 64) {
+                    if (np == 2) launch_conv_slab<64, 2, 1>(rt.mapSlab, mc.mapB, rt.mapOut[0], p, tiles, num_sms, s);
+                    else launch_conv_slab<64, 1, 1>(rt.mapSlab, mc.mapB, rt.mapOut[0], p, tiles, num_sms, s);
+                } else if (np == 2) {
                     if (cl == 4) launch_conv_slab<128, 2, 4>(rt.mapSlab, mc.mapBmc[1], rt.mapOut[0], p, tiles, num_sms, s);
                     else if (cl == 2) launch_conv_slab<128, 2, 2>(rt.mapSlab, mc.mapBmc[0], rt.mapOut[0], p, tiles, num_sms, s);
                     else launch_conv_slab<128, 2, 1>(rt.mapSlab, mc.mapB, rt.mapOut[0], p, tiles, num_sms, s);

@@ -53,7 +53,8 @@ struct ConvSpec {
     std::vector<MapReq> maps;
     bool kcat = false;                 // parts are concatenated along K (one part per source; BN scales folded into the weights):
                                        // out = act(sum_p BN_p(conv_p(src_p))) -- the ResNet shortcut conv fused into branch2c
-    bool slab = false;                 // runs on conv_tc_slab_kernel (k x k stride-1 conv, Cout 128, W % 8 == 0, H % 16 == 0)
+    bool slab = false;                 // runs on conv_tc_slab_kernel (k x k stride-1 conv, Cout 128, W % 8 == 0, H % 16 == 0; or the heads)
+    int slab_ks = 0;                   // tap grid of the slab formulation (= ksize; 3 for the phase-fused heads: 3x3 input neighbourhood)
     std::vector<int4> slabs;           // slab kernel: one entry per (source, 64-channel chunk)
 };
 

@@ -197,14 +197,17 @@ P2P_HD inline double cv_hypot(double a, double b) {   // lapack.cpp's local hypo
 #define P2P_UNROLL
 #define P2P_NOINLINE
 #endif
-template <int S>
-P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, double* Vt, int n1) {
+// Row length M is a compile-time constant (3 and 6 on the device: two copies of the code), so the two rows of a pair sit in
+// registers while they are rotated; N, the pair loops and the V update stay run-time loops over the strided scratch.
+template <int S, int M>
+P2P_HD P2P_NOINLINE void cv_jacobi_svd_m(double* At, int N, double* W, double* Vt, int n1) {
     const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
 #define P2P_AT(i, k) At[((i) * M + (k)) * S]
 #define P2P_VT(i, k) Vt[((i) * N + (k)) * S]
 #define P2P_W(i) W[(i) * S]
     for (int i = 0; i < N; ++i) {
         double sd = 0;
+        P2P_UNROLL
         for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
         P2P_W(i) = sd;
         if (Vt)
@@ -215,8 +218,14 @@ P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, doub
         bool changed = false;
         for (int i = 0; i < N - 1; ++i)
             for (int j = i + 1; j < N; ++j) {
+                double ri[M], rj[M];
                 double a = P2P_W(i), p = 0, b = P2P_W(j);
-                for (int k = 0; k < M; ++k) p += P2P_AT(i, k) * P2P_AT(j, k);
+                P2P_UNROLL
+                for (int k = 0; k < M; ++k) {
+                    ri[k] = P2P_AT(i, k);
+                    rj[k] = P2P_AT(j, k);
+                    p += ri[k] * rj[k];
+                }
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
                 const double beta = a - b, gamma = cv_hypot(p, beta);
@@ -230,10 +239,10 @@ P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, doub
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+                P2P_UNROLL
                 for (int k = 0; k < M; ++k) {
-                    const double x = P2P_AT(i, k), y = P2P_AT(j, k);
-                    const double t0 = c * x + s * y;
-                    const double t1 = -s * x + c * y;
+                    const double t0 = c * ri[k] + s * rj[k];
+                    const double t1 = -s * ri[k] + c * rj[k];
                     P2P_AT(i, k) = t0;
                     P2P_AT(j, k) = t1;
                     a += t0 * t0;
@@ -253,6 +262,7 @@ P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, doub
     }
     for (int i = 0; i < N; ++i) {
         double sd = 0;
+        P2P_UNROLL
         for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); sd += t * t; }
         P2P_W(i) = sqrt(sd);
     }
@@ -262,6 +272,7 @@ P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, doub
             if (P2P_W(j) < P2P_W(k)) j = k;
         if (i != j) {
             const double tw = P2P_W(i); P2P_W(i) = P2P_W(j); P2P_W(j) = tw;
+            P2P_UNROLL
             for (int k = 0; k < M; ++k) { const double t = P2P_AT(i, k); P2P_AT(i, k) = P2P_AT(j, k); P2P_AT(j, k) = t; }
             if (Vt)
                 for (int k = 0; k < N; ++k) { const double t = P2P_VT(i, k); P2P_VT(i, k) = P2P_VT(j, k); P2P_VT(j, k) = t; }
@@ -296,11 +307,22 @@ P2P_HD P2P_NOINLINE void cv_jacobi_svd(double* At, int M, int N, double* W, doub
             sd = sqrt(sd);
         }
         const double sc = sd > minval ? 1 / sd : 0.;
+        P2P_UNROLL
         for (int k = 0; k < M; ++k) P2P_AT(i, k) *= sc;
     }
 #undef P2P_AT
 #undef P2P_VT
 #undef P2P_W
+}
+
+// run-time row length: 3 and 6 are what EPnP uses; 12 only in the host tests (the device has cv_jacobi_svd12_ut)
+template <int S>
+P2P_HD inline void cv_jacobi_svd(double* At, int M, int N, double* W, double* Vt, int n1) {
+    if (M == 3) cv_jacobi_svd_m<S, 3>(At, N, W, Vt, n1);
+    else if (M == 6) cv_jacobi_svd_m<S, 6>(At, N, W, Vt, n1);
+#if !defined(__CUDA_ARCH__)
+    else if (M == 12) cv_jacobi_svd_m<S, 12>(At, N, W, Vt, n1);
+#endif
 }
 
 // The same routine specialised for what EPnP asks of the 12 x 12 M^T M (U^T only), laid out for a GPU thread: row i

@@ -214,11 +214,11 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
 // again and the result depends on every rounding, so one thread per problem runs OpenCV's exact serial operation order
 // on the inliers in index order (solve_small, the routine of the hypothesis kernel; workspace in shared memory).
 constexpr int kSmallThreads = 32;
-__global__ void __launch_bounds__(kSmallThreads) epnp_refit_small_kernel(const PnpProblem* __restrict__ probs, int n_problems,
-                                                                        const float* __restrict__ obj, const float* __restrict__ img,
-                                                                        const int* __restrict__ small_list, PnpResult* __restrict__ res) {
-    __shared__ double s_ws[144 * kSmallThreads];
-    const int p = blockIdx.x * kSmallThreads + threadIdx.x;
+__device__ __forceinline__ void refit_small_block(int block, const PnpProblem* __restrict__ probs, int n_problems,
+                                                  const float* __restrict__ obj, const float* __restrict__ img,
+                                                  const int* __restrict__ small_list, PnpResult* __restrict__ res, double* s_ws) {
+    if (threadIdx.x >= kSmallThreads) return;
+    const int p = block * kSmallThreads + threadIdx.x;
     if (p >= n_problems) return;
     const PnpProblem pr = probs[p];
     PnpResult* out = res + p;
@@ -268,11 +268,20 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red, double* s
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpProblem* __restrict__ probs,
+// Blocks 0 .. n_problems-1: one problem each (block reductions over its inliers).  The blocks after them run the exact serial
+// refits of the small consensus sets (4a), 32 problems per block, CONCURRENTLY with the large ones: both are bound by one
+// thread's serial latency, so as separate launches they simply added up (0.6 + 1.0 ms per 768 problems).
+__global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpProblem* __restrict__ probs, int n_problems,
                                                                    const float* __restrict__ obj, const float* __restrict__ img,
-                                                                   const uint8_t* __restrict__ mask, PnpResult* __restrict__ res) {
-    __shared__ double s_red[(kRefitThreads / 32) * 52];
-    __shared__ double s_sum[52];
+                                                                   const uint8_t* __restrict__ mask, const int* __restrict__ small_list,
+                                                                   PnpResult* __restrict__ res) {
+    __shared__ double s_small[144 * kSmallThreads];   // workspace of the small-set blocks; the large ones use its first 2 KB
+    if (static_cast<int>(blockIdx.x) >= n_problems) {
+        refit_small_block(static_cast<int>(blockIdx.x) - n_problems, probs, n_problems, obj, img, small_list, res, s_small);
+        return;
+    }
+    double* s_red = s_small;                          // [(kRefitThreads / 32) * 52]
+    double* s_sum = s_small + (kRefitThreads / 32) * 52;   // [52]
     __shared__ double s_cws[4][3], s_ci[9], s_R[3][3][3], s_t[3][3];
     __shared__ int s_first;
     const PnpProblem pr = probs[blockIdx.x];
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpP
         }
         return;
     }
-    if (out->n_mask <= kSmallRefit) return;   // epnp_refit_small_kernel's case
+    if (out->n_mask <= kSmallRefit) return;   // refitted by the small-set blocks
     const float* o = obj + pr.offset * 3;
     const float* ip = img + pr.offset * 2;
     const uint8_t* mk = mask + pr.offset;
@@ -450,10 +459,8 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
                                                     small_.p, results_dev, iters, thr2, confidence);
     P2P_CUDA(cudaGetLastError());
     mark(3);
-    epnp_refit_small_kernel<<<(n_problems + kSmallThreads - 1) / kSmallThreads, kSmallThreads, 0, s>>>(problems_dev, n_problems, obj_dev,
-                                                                                                       img_dev, small_.p, results_dev);
-    P2P_CUDA(cudaGetLastError());
-    epnp_refit_kernel<<<n_problems, kRefitThreads, 0, s>>>(problems_dev, obj_dev, img_dev, mask_dev, results_dev);
+    epnp_refit_kernel<<<n_problems + (n_problems + kSmallThreads - 1) / kSmallThreads, kRefitThreads, 0, s>>>(
+        problems_dev, n_problems, obj_dev, img_dev, mask_dev, small_.p, results_dev);
     P2P_CUDA(cudaGetLastError());
     mark(4);
     if (prof) {
@@ -463,7 +470,7 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         fprintf(stderr, "pnp[%d problems] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, ms[0], ms[1], ms[2], ms[3]);
         for (auto e : ev) cudaEventDestroy(e);
     }
-    launches += 5;
+    launches += 4;
 }
 
 void PnpSolver::solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,

@@ -298,14 +298,14 @@ def test_device_mask_iou_matches_numpy(rec, frame):
 
 
 def test_tless_like_stream_per_object_thresholds():
-    """SURVEY section 8d config 5 in miniature: 720x540 frames, the paper backbone, one outlier threshold PER OBJECT handed over
-    as a nested list (cfg_tless_paper.json:12, 5_evaluation_bop_basic.py:217), all objects' detections in one device run:
-    every detection gets exactly what its own object's recogniser returns for it alone."""
+    """SURVEY section 8d config 5 in miniature: 720x540 frames, one outlier threshold PER OBJECT handed over as a nested list
+    (cfg_tless_paper.json:12, 5_evaluation_bop_basic.py:217), all objects' detections in one device run: every detection
+    gets exactly what its own object's recogniser returns for it alone."""
     from pix2pose_b200.stream import MultiObjectRecognizer
-    ths = {1: [[0.1]], 4: [[0.3]], 5: [[0.2]]}
+    ths = {1: [[0.15]], 4: [[0.3]], 5: [[0.2]]}
     objs = {1: np.array([50., 40., 60., 0., 0., 0.]), 4: np.array([30., 30., 80., 1., -2., 3.]), 5: np.array([45., 45., 20., 0., 5., 0.])}
-    wts = {o: W.synthetic_weights("paper", o) for o in ths}
-    multi = MultiObjectRecognizer(wts, K_TLESS, 720, 540, objs, th_outlier=ths, th_inlier=0.1, backbone="paper", capacity=16, max_dets=32)
+    wts = {o: W.synthetic_weights("resnet50", o) for o in ths}
+    multi = MultiObjectRecognizer(wts, K_TLESS, 720, 540, objs, th_outlier=ths, th_inlier=0.15, backbone="resnet50", capacity=16, max_dets=32)
     rng = np.random.RandomState(8)
     frames = rng.randint(0, 256, (2, 540, 720, 3)).astype(np.uint8)
     rois, oids, fids = [], [], []
