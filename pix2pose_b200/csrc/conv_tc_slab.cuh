@@ -24,20 +24,24 @@ template <int BN, int NP>
 struct SlabCfg {
     static constexpr int SLAB_W = 8;
     static constexpr int TILE_H = 16;
-    // BN = 16 (the heads: 3 x 3 taps only): one halo row above and below, and a DEEP slab ring -- a slab feeds just 3 taps of
-    // 8 narrow MMAs (~300 cycles), far less than a TMA round trip, so two buffers left the tensor pipe waiting for loads
-    // (heads 360 -> 414 us per 256 crops with 2 buffers).  The wide convs (5 x 5: 25 taps x 8 wide MMAs per slab column) hide
-    // the latency with two.
-    static constexpr int MAX_ROWS = BN < 64 ? TILE_H + 2 : TILE_H + 4;
+    // BN = 16 (the heads: 3 x 3 taps, 128 input channels, 16 accumulator columns).  A slab feeds only 3 taps x 8 narrow MMAs
+    // (a few hundred cycles of tensor work), far less than a TMA round trip, so the layer was bound by how many operand
+    // stages are in flight, not by MMAs or bytes: the generic 6-stage ring gave ~690 cycles per tap (heads 360 us per 256
+    // crops; 414 us on this kernel with a 2-deep slab ring and the 6-stage weight ring).  Here ALL the layer's weights
+    // (18 k-iterations x 4 KB) are loaded once per CTA and stay resident (RES_B), so the only ring is the slab ring, 4 deep.
+    static constexpr bool RES_B = BN < 64;
+    static constexpr int RES_KITERS = 18;                             // resident weight tiles (2 chunks x 9 taps)
+    static constexpr int MAX_ROWS = RES_B ? TILE_H + 2 : TILE_H + 4;   // halo rows above and below: k = 3 / k <= 5
     static constexpr int SLAB_BYTES = NP * SLAB_W * MAX_ROWS * 128;   // 40 KB (fp16x3, k <= 5), 36 KB (heads)
-    static constexpr int SLAB_BUFS = BN < 64 ? (NP == 2 ? 5 : 6) : 2;
+    static constexpr int SLAB_BUFS = RES_B ? 4 : 2;
     static constexpr int B_BYTES = NP * BN * 128;
-    static constexpr int EPI_BYTES = BN < 64 ? 0 : NP * 128 * 128;    // the heads store fp32 straight from registers
+    static constexpr int EPI_BYTES = RES_B ? 0 : NP * 128 * 128;      // the heads store fp32 straight from registers
     static constexpr int B_ROOM = 224 * 1024 - SLAB_BUFS * SLAB_BYTES - EPI_BYTES - 2048;
-    static constexpr int B_STAGES = B_ROOM / B_BYTES > 6 ? 6 : B_ROOM / B_BYTES;
+    static constexpr int B_STAGES = RES_B ? RES_KITERS : (B_ROOM / B_BYTES > 6 ? 6 : B_ROOM / B_BYTES);
     static constexpr int CONST_BYTES = 2 * (BN < 64 ? 64 : BN) * 4;
     static constexpr int SMEM_BYTES = SLAB_BUFS * SLAB_BYTES + B_STAGES * B_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CONST_BYTES;
-    static_assert(B_STAGES >= 2, "no room for the weight ring");
+    static_assert(B_STAGES >= 2 && SMEM_BYTES <= 227 * 1024, "shared-memory plan does not fit");
+    static_assert((2 * (RES_B ? 1 : B_STAGES) + 2 * SLAB_BUFS + 4) * 8 + 4 <= 256, "barrier area");
 };
 
 // slab table entry (p.kit): {map index | (k16 steps << 8), first channel, first packed-weight k-iteration of
@@ -84,8 +88,9 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
     uint8_t* sB = smem + SC::SLAB_BUFS * SC::SLAB_BYTES;
     uint8_t* sEpi = sB + BS * SC::B_BYTES;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(sEpi + SC::EPI_BYTES);
-    uint64_t* b_empty = b_full + BS;
-    uint64_t* slab_full = b_empty + BS;
+    constexpr int NBB = SC::RES_B ? 1 : BS;   // weight-ring barriers (resident weights: one "all landed" barrier)
+    uint64_t* b_empty = b_full + NBB;
+    uint64_t* slab_full = b_empty + NBB;
     uint64_t* slab_empty = slab_full + SC::SLAB_BUFS;
     uint64_t* tmem_full_bar = slab_empty + SC::SLAB_BUFS;  // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
@@ -95,7 +100,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mS0);
         tma_prefetch_desc(&mB);
-        for (int s = 0; s < BS; ++s) {
+        for (int s = 0; s < NBB; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], CL);  // the MMA warp of every CTA in the cluster
         }
@@ -123,6 +128,14 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
         // ===================== TMA producer (whole warp convergent, TMA issue under elect_one) =====================
         int bs = 0, ss = 0;
         uint32_t bph = 0, sph = 0;
+        if (SC::RES_B) {
+            // every weight tile of the layer, once (the host checked that they fit: n_slabs * ks * ks <= RES_KITERS)
+            const int nk = n_slabs * ks * ks;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(nk) * SC::B_BYTES);
+                for (int kiter = 0; kiter < nk; ++kiter) tma_load_4d(&mB, &b_full[0], sB + kiter * SC::B_BYTES, 0, 0, 0, kiter);
+            }
+        }
         for (int g = group0; g < total_groups; g += ngroups) {
             const TileCoord tc = decode_tile<BN>(p, tile_of(g), n_limit);
             if (!decode_tile<BN>(p, g * CL, n_limit).live) continue;  // one decision per cluster
@@ -136,6 +149,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
                         tma_load_5d(mS, &slab_full[ss], sSlab + ss * SC::SLAB_BYTES, k.y, tc.x0 - pad + dx, tc.y0 - pad, tc.n0, 0);
                     }
                     if (++ss == SC::SLAB_BUFS) { ss = 0; sph ^= 1; }
+                    if (SC::RES_B) continue;
                     for (int dy = 0; dy < ks; ++dy) {
                         mbar_wait(&b_empty[bs], bph ^ 1);
                         if (elect_one()) {
@@ -166,6 +180,10 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
         const uint32_t slab0 = smem_u32(sSlab), b0 = smem_u32(sB);
         int bs = 0, ss = 0, tile_i = 0;
         uint32_t bph = 0, sph = 0;
+        if (SC::RES_B) {
+            mbar_wait(&b_full[0], 0);   // the resident weights have landed
+            tc_fence_after();
+        }
         for (int g = group0; g < total_groups; g += ngroups) {
             if (!decode_tile<BN>(p, g * CL, n_limit).live) continue;
             const uint32_t buf = tile_i & 1, use = tile_i >> 1;
@@ -175,15 +193,18 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
             int gk = 0;  // k16 steps issued for this tile
             for (int sl = 0; sl < n_slabs; ++sl) {
                 const int ksteps = p.ksteps_tab[sl];
+                const int4 kent = __ldg(&p.kit[sl]);
                 for (int dx = 0; dx < ks; ++dx) {
                     mbar_wait(&slab_full[ss], sph);
                     tc_fence_after();
                     const uint32_t aSlab = slab0 + ss * SC::SLAB_BYTES;
                     for (int dy = 0; dy < ks; ++dy) {
-                        mbar_wait(&b_full[bs], bph);
-                        tc_fence_after();
+                        if (!SC::RES_B) {
+                            mbar_wait(&b_full[bs], bph);
+                            tc_fence_after();
+                        }
                         const uint32_t aA = aSlab + dy * SC::SLAB_W * 128;  // 1024-byte aligned for every dy
-                        const uint32_t aB = b0 + bs * SC::B_BYTES;
+                        const uint32_t aB = b0 + (SC::RES_B ? kent.z + (dy * ks + dx) * kent.w : bs) * SC::B_BYTES;
                         const uint64_t dA = umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
                         const uint64_t dAlo = umma_desc_sw128(aA + plane_off), dBlo = umma_desc_sw128(aB + BN * 128);
                         if (elect_one()) {   // one elected region per tap (see conv_tc_persistent.cuh)
@@ -210,11 +231,13 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mS0, const __grid_consta
                             }
                         }
                         gk += ksteps;
-                        if (elect_one()) {
-                            if (CL == 1) umma_commit(&b_empty[bs]);
-                            else umma_commit_mc(&b_empty[bs], kAll);  // this stage is shared: free it in every CTA
+                        if (!SC::RES_B) {
+                            if (elect_one()) {
+                                if (CL == 1) umma_commit(&b_empty[bs]);
+                                else umma_commit_mc(&b_empty[bs], kAll);  // this stage is shared: free it in every CTA
+                            }
+                            if (++bs == BS) { bs = 0; bph ^= 1; }
                         }
-                        if (++bs == BS) { bs = 0; bph ^= 1; }
                     }
                     if (elect_one()) umma_commit(&slab_empty[ss]);  // frees the slab once its k vertical taps have retired
                     if (++ss == SC::SLAB_BUFS) { ss = 0; sph ^= 1; }

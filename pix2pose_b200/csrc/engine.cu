@@ -985,6 +985,9 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 for (int i = 1; i < 5; ++i) p.kstart[i] = static_cast<int>(c.slabs.size());
                 for (size_t i = 0; i < c.slabs.size(); ++i) p.ksteps_tab[i] = static_cast<uint8_t>(c.slabs[i].x >> 8);
                 const int tiles = static_cast<int>(grid.x * grid.y);
+                constexpr int res_kiters = SlabCfg<16, 2>::RES_KITERS;
+                P2P_CHECK(static_cast<int>(c.slabs.size()) * c.slab_ks * c.slab_ks <= res_kiters,
+                          "heads: %zu weight tiles do not fit the resident buffer", c.slabs.size() * c.slab_ks * c.slab_ks);
                 if (np == 2) launch_conv_slab<16, 2, 1>(rt.mapSlab, mc.mapB, rt.mapSlab[0], p, tiles, num_sms, s);   // (no output map: fp32 stores)
                 else launch_conv_slab<16, 1, 1>(rt.mapSlab, mc.mapB, rt.mapSlab[0], p, tiles, num_sms, s);
             } else if (slab && c.slab && rt.has_out && tma_store) {

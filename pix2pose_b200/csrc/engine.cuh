@@ -106,7 +106,7 @@ class Engine {
     int num_sms = 148;
     bool prof_layers = false; // print per-launch times in profile mode (P2P_PROF_LAYERS)
     int epi_nk = 8;           // layers with at most this many k-iterations per tile trade operand stages for output staging tiles (P2P_EPI_NK)
-    int single_acc_steps = 40;  // accumulation chains up to this many k16 steps use one TMEM accumulator (P2P_SINGLE_ACC_STEPS)
+    int single_acc_steps = 0;   // accumulation chains up to this many k16 steps use ONE TMEM accumulator (P2P_SINGLE_ACC_STEPS).  0 = never: below N = 256 an MMA costs ~75 cycles whatever its width (the 4 KB A-operand read), so the widened two-MMA form (N = 2 BN, then BN) beats three MMAs of width BN also on short chains (3x3 64-ch convs 78 -> 70 us per 256 crops)
     bool res_tma = true;      // residual tiles by TMA into shared memory (P2P_RES_TMA=0 = per-thread loads)
     bool tma_store = true;    // TMA-store epilogue in the persistent kernel (default; P2P_TMA_STORE=0 = direct 16-byte stores)
     int slab_cluster = 1;     // CTAs sharing every weight stage by TMA multicast in the slab kernel (P2P_SLAB_CLUSTER=1|2|4; measured:
