@@ -152,6 +152,10 @@ P2P_API int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const floa
 /* box_size of pix2pose.__init__ (recognition.py:10, :19; used by get_boxes :33-34 for the stage-1 box and for the
  * refined boxes :110).  Applies to the following runs; default 1.5. */
 P2P_API int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size);
+/* Test hook: candidate selection (recognition.py:158-178, :189-193) of the last run repeated with caller-supplied PnP results
+ * for its n_cands compact candidates (Rt: 12 doubles each = R row-major, t; n_inliers; status 1 = pose, 0 = inliers None). */
+P2P_API int p2p_pipeline_debug_select(p2p_pipeline_t* p, const double* Rt, const int* n_inliers, const int* status, int n_cands,
+                              int n, p2p_pose_t* out);
 P2P_API long long p2p_pipeline_launch_count(const p2p_pipeline_t* p);
 /* Measurement: device milliseconds the generator forwards (recognition.py:84 and :129) of the LAST run took, from CUDA
  * event nodes recorded around them inside the run itself (they are part of the captured graph). */

@@ -214,6 +214,13 @@ int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size) {
         p->p->box_size = box_size;
     });
 }
+int p2p_pipeline_debug_select(p2p_pipeline_t* p, const double* Rt, const int* n_inliers, const int* status, int n_cands, int n,
+                              p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->debug_select(Rt, n_inliers, status, n_cands, n, reinterpret_cast<PoseRecord*>(out));
+    });
+}
 int p2p_pipeline_forward_ms(p2p_pipeline_t* p, double* ms) {
     return guarded([&] {
         P2P_CHECK(p && ms, "NULL argument");

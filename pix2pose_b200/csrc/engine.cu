@@ -354,10 +354,12 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
         c.slab = true;
         c.slab_ks = c.ksize;
     }
-    // The heads (phase-fused transposed conv, N = 16) are a 3 x 3 stride-1 conv over d3_uni from the GEMM's point of view and
-    // were bound by re-fetching the 128-pixel activation tile for each of the 9 taps (9 x 537 MB through L2 per 256 crops for
-    // 1 % of the FLOPs); on the slab kernel a tile's activations arrive 3 x instead of 9 x.
-    static const bool slab_heads = !getenv("P2P_SLAB_HEADS") || atoi(getenv("P2P_SLAB_HEADS")) != 0;
+    // The heads (phase-fused transposed conv, N = 16) are a 3 x 3 stride-1 conv over d3_uni from the GEMM's point of view, so
+    // they CAN run on the slab kernel (activations fetched 3 x instead of 9 x, weights resident in shared memory).  Measured:
+    // no gain (365 us generic, 376 us slab per 256 crops) -- the layer is bound by its 144 MMAs per 128-pixel tile at ~87
+    // cycles each (an M = 128 MMA reads its 4 KB A operand from shared memory at ~64 B/clk whatever N is), not by operand
+    // traffic or load latency.  Kept as an experiment: P2P_SLAB_HEADS=1.
+    static const bool slab_heads = getenv("P2P_SLAB_HEADS") && atoi(getenv("P2P_SLAB_HEADS")) != 0;
     if (slab_on && slab_heads && c.kind == K_CONVT_FUSED && c.act == ACT_HEADS && c.W % 8 == 0 && c.H % 16 == 0 && c.srcs.size() == 1) {
         c.slab = true;
         c.slab_ks = 3;

@@ -784,6 +784,30 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
     memcpy(out, pinned_recs_, sizeof(PoseRecord) * n);
 }
 
+void Pipeline::debug_select(const double* Rt, const int* n_inliers, const int* status, int n_cands, int n, PoseRecord* out) {
+    // parity hook: candidate selection (recognition.py:158-178, :189-193) re-run on the LAST run's candidates with PnP
+    // results supplied by the caller (e.g. cv2's own per-candidate R|t), everything else as the device computed it
+    P2P_CHECK(Rt && n_inliers && status && out, "NULL argument");
+    P2P_CHECK(n >= 1 && n <= static_cast<int>(host_dets_.size()) && n_cands >= 0 && n_cands <= n * n_th, "debug_select: bad counts");
+    cudaStream_t s = engine->stream;
+    std::vector<PnpResult> h(static_cast<size_t>(n) * n_th);
+    P2P_CUDA(cudaMemcpyAsync(h.data(), pnp_res_.p, sizeof(PnpResult) * h.size(), cudaMemcpyDeviceToHost, s));
+    P2P_CUDA(cudaStreamSynchronize(s));
+    for (int c = 0; c < n_cands; ++c) {
+        PnpResult& r = h[c];
+        for (int i = 0; i < 9; ++i) r.R[i] = Rt[c * 12 + i];
+        for (int i = 0; i < 3; ++i) r.tvec[i] = Rt[c * 12 + 9 + i];
+        r.n_inliers = n_inliers[c];
+        r.status = status[c];
+    }
+    DevBuf<PnpResult> tmp(h.size());
+    P2P_CUDA(cudaMemcpyAsync(tmp.p, h.data(), sizeof(PnpResult) * h.size(), cudaMemcpyHostToDevice, s));
+    select_kernel<<<(n + 127) / 128, 128, 0, s>>>(dets_.p, state_.p, cands_.p, tmp.p, recs_.p, n);
+    P2P_CUDA(cudaGetLastError());
+    P2P_CUDA(cudaMemcpyAsync(out, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
+    P2P_CUDA(cudaStreamSynchronize(s));
+}
+
 double Pipeline::forward_ms() {
     // events 0-1 bracket the stage-1 forwards, 2-3 the stage-2 forwards of the last run
     P2P_CHECK(fwd_ev_.size() >= 4 && last_n_fwd_ev_ == 4, "forward_ms: no run yet");

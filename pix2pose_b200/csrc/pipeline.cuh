@@ -94,6 +94,9 @@ class Pipeline {
     // Test hook: replace the network outputs of `stage` (1|2) in the NEXT run by these host arrays
     // (n crops of decode (128,128,3) and prob (128,128)); used by planted-pose parity tests only.
     void set_override(int stage, const float* dec, const float* prob, int n);
+    // Test hook: re-run the candidate selection of the last run with caller-supplied PnP results (n_cands compact candidates:
+    // R row-major 9 + t 3 per candidate, inlier count, status 1 / 0) -> records of the first n detections.
+    void debug_select(const double* Rt, const int* n_inliers, const int* status, int n_cands, int n, PoseRecord* out);
     // Host frames (F,H,W,3) uint8 / float32 -> device copy owned by the pipeline.
     const void* upload_frames(const void* frames_host, bool f32, int F, int H, int W);
     // Device milliseconds the generator forwards of the last run took (stage 1 + stage 2; event nodes inside the run).

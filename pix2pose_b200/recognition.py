@@ -323,6 +323,18 @@ class pix2pose():
         decode, prob = _lib.as_f32(decode), _lib.as_f32(prob)
         _lib.check(_lib.lib().p2p_pipeline_debug_override(self._pipeline(n_dets), stage, _lib.fptr(decode), _lib.fptr(prob), decode.shape[0]))
 
+    def debug_select(self, Rt, n_inliers, status):
+        """Parity hook: repeats the candidate selection of this object's last single-detection run with the given
+        per-candidate PnP results (``Rt`` (k,12): R row-major then t) and returns the resulting pose record."""
+        Rt = np.ascontiguousarray(np.asarray(Rt, np.float64).reshape(-1, 12))
+        ni = np.ascontiguousarray(np.asarray(n_inliers, np.int32))
+        st = np.ascontiguousarray(np.asarray(status, np.int32))
+        pose = (_Pose * 1)()
+        _lib.check(_lib.lib().p2p_pipeline_debug_select(self._live_pipe(), Rt.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                        ni.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                                        st.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(ni), 1, pose))
+        return pose[0]
+
     def _fetch_pred(self, stage, index, zero_gray):
         dec = np.zeros((128, 128, 3), np.float32)
         _lib.check(_lib.lib().p2p_pipeline_fetch_decode(self._live_pipe(), stage, index, _lib.fptr(dec)))

@@ -11,6 +11,8 @@ not name-based).  Names are ours; layouts are Keras':
 * Dense             ``kernel (in,out)``, ``bias (out,)``
 * BatchNormalization ``gamma, beta, moving_mean, moving_variance`` each ``(C,)``
 """
+import re
+
 import numpy as np
 
 CONV, CONVT, DENSE, BN = "conv", "convT", "dense", "bn"
@@ -182,6 +184,10 @@ def _keras_file_layers(f):
     return out
 
 
+# layer names given in the reference's model code: resnet50_mod.py:59-114, 200-202; ae_model.py:74-103, 118-138, 190-228
+_EXPLICIT = re.compile(r"^(conv1|bn_conv1|res\d[a-z]_branch\w+|bn\d[a-z]_branch\w+|conv[1-4]_[12]|deconv[1-3])$")
+
+
 def keras_layers_to_weights(file_layers, backbone):
     """Maps the ordered layers of a Keras file onto ``param_names(backbone)``.  Layers the reference names explicitly
     (``conv1``, ``bn_conv1``, ``res2a_branch2a`` ..., ``conv4_1`` ...; resnet50_mod.py:60-118, ae_model.py:74-106,
@@ -211,7 +217,12 @@ def keras_layers_to_weights(file_layers, backbone):
                 raise ValueError("layer %s (file layer %s) has no %r" % (name, src, k))
             out[name + "/" + k] = np.asarray(w[k], np.float32)
 
-    for name, kind, _ in table:                      # pass 1: explicit names
+    for name, kind, _ in table:                      # pass 1: the names the reference sets explicitly, and only those --
+        # our table's own names for auto-named Keras layers ('dense_1', 'dense_2', ...) collide with Keras' counters: a file
+        # saved by a process that had built another Dense before holds 'dense_2' / 'dense_3', and matching 'dense_2' by name
+        # would pair the wrong kernels where Keras' order-based load_weights pairs the right ones
+        if not _EXPLICIT.match(name):
+            continue
         if name in by_name and kind_of(name, by_name[name]) in (kind, CONV if kind == CONVT else kind):
             put(name, kind, by_name[name], name)
             used.add(name)

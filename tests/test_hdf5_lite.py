@@ -73,7 +73,7 @@ def test_backbone_roundtrip_through_keras_layout(tmp_path):
     assert all(np.array_equal(w[k], got[k]) for k in W.param_names("paper"))
 
 
-def _keras_style_resnet50_file(path, w):
+def _keras_style_resnet50_file(path, w, counter_shift=0):
     """The file Keras 2.2.1 writes for aemodel_unet_resnet50 (ae_model.py:175-240): layer_names in topological order,
     the ResNet part as ONE nested model layer whose weight_names follow graph depth (branch2c and the shortcut conv
     branch1 at the same depth, their BatchNorms after both), decoder layers auto-named."""
@@ -115,7 +115,7 @@ def _keras_style_resnet50_file(path, w):
             kname = name
         else:
             cnt[kind] += 1
-            kname = auto[kind] % cnt[kind]
+            kname = auto[kind] % (cnt[kind] + counter_shift)
         wn = []
         for k in keys(kind):
             f.create_dataset("%s/%s/%s:0" % (kname, kname, k), w[name + "/" + k])
@@ -137,3 +137,15 @@ def test_keras_style_resnet50_file_maps_onto_the_layer_table(tmp_path):
     with hdf5_lite.File(p) as f:
         layers = W._keras_file_layers(f)
     assert layers[0][0] == "conv1" and "kernel" in layers[0][1]
+
+
+def test_shifted_keras_auto_name_counters_still_map_by_order(tmp_path):
+    """A file saved by a process that had built another model first carries shifted auto-names (dense_2 / dense_3,
+    batch_normalization_9 ...).  Keras' load_weights pairs such layers by ORDER; so must the importer -- in particular the
+    file's 'dense_2' (32768 x 256) must not be matched by name with the table's dense_2 (256 x 16384)."""
+    w = W.synthetic_weights("resnet50", 4)
+    p = str(tmp_path / "shifted.hdf5")
+    _keras_style_resnet50_file(p, w, counter_shift=1)
+    got = W.load_keras_hdf5(p, "resnet50")
+    bad = [k for k in W.param_names("resnet50") if not np.array_equal(w[k], got[k])]
+    assert not bad, bad[:5]

@@ -349,3 +349,100 @@ def test_graph_replay_equals_plain_launches(rec, frame):
     l0 = rec.launch_count
     rec.est_pose_batch(frame, rois)
     assert rec.launch_count - l0 >= 80           # replays still count their kernels (bench.py's gpu_launches): 2 forwards of 35 + 11
+
+
+@pytest.mark.parametrize("seed,roi,rv,t", [(0, [182, 290, 286, 386], [0.4, -0.3, 0.2], [15.0, -10.0, 700.0]),
+                                           (2, [300, 420, 470, 630], [0.1, 0.9, -0.4], [180.0, 140.0, 800.0])])
+def test_candidate_selection_fed_with_cv2_results(rec, frame, seed, roi, rv, t):
+    """A18 in isolation (recognition.py:158-178, :189-193): the device selection is re-run on the candidates of a planted
+    run with the PnP results of the ORACLE (cv2's own R|t and inlier count per candidate, bit for bit) and must then return
+    exactly the oracle's choice: the same R|t bits, inlier fraction and bbox_t -- including a variant where PnP failed for
+    the would-be winner (t = 0 -> dist 99999, recognition.py:163-165) and one where it returned inliers = None (:219)."""
+    from oracle.recognition_oracle import Pix2PoseOracle
+    R, t = rodrigues(rv), np.array(t)
+    want, s1, s2, ora = planted_case(Pix2PoseOracle, frame, roi, R, t, seed=seed, **TH)
+    rec.debug_override(1, s1[0], s1[1])
+    rec.debug_override(2, s2[0], s2[1])
+    rec.est_pose(frame, np.array(roi))
+    cands = ora.trace["cands"]
+    assert len(cands) >= 2
+    K = K_LM
+
+    def reference_choice(cs):               # recognition.py:158-178 on the per-candidate values
+        best, min_dist, max_inl = None, 9999999, -1
+        for c in cs:
+            if c["t"][2] == 0:
+                dist = 99999
+            else:
+                dist = c["dist"] if c.get("dist_override") is None else c["dist_override"]
+            if dist < min_dist:
+                best, min_dist, max_inl = c, dist, c["n_inliers"]
+        return best, max_inl
+
+    for variant in ("as_is", "winner_pnp_failed", "winner_no_inliers"):
+        cs = [dict(c) for c in cands]
+        win0, _ = reference_choice(cs)
+        if variant == "winner_pnp_failed":          # pnp_ransac's `n_pts < 6` return: eye(3), zeros, -1 inliers (:214-215)
+            win0["R"], win0["t"], win0["n_inliers"] = np.eye(3), np.zeros(3), -1
+        elif variant == "winner_no_inliers":        # inliers is None: eye(3), zeros, valid_mask -1, -1 (:218-219)
+            win0["R"], win0["t"], win0["n_inliers"], win0["none"] = np.eye(3), np.zeros(3), -1, True
+        Rt = np.array([np.concatenate([np.asarray(c["R"], float).ravel(), np.asarray(c["t"], float).ravel()]) for c in cs])
+        ninl = [int(c["n_inliers"]) for c in cs]
+        # status 1 = pose with inliers; 0 = the reference's "inliers is None" return; a failed pnp (-1 inliers, t = 0) also arrives as 0
+        status = [1 if c["n_inliers"] >= 0 else 0 for c in cs]
+        pose = rec.debug_select(Rt, ninl, status)
+        best, max_inl = reference_choice(cs)
+        if max_inl == -1:
+            assert pose.status != 1
+            continue
+        assert pose.status == 1 and pose.best_cand == best["cid"], variant
+        assert np.array_equal(np.array(list(pose.R)).reshape(3, 3), np.asarray(best["R"], float)), variant
+        assert np.array_equal(np.array(list(pose.t)), np.asarray(best["t"], float).ravel()), variant
+        assert pose.n_inliers == max_inl
+        assert list(pose.bbox_t) == list(want[5])
+
+
+def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
+    """Oracle generator (torch-CPU fp32) -> oracle pipeline against GPU generator -> GPU pipeline, on REAL network outputs
+    (VERDICT r1, weak #3).  The two generators agree to ~2e-4 (tests/test_net_gpu.py), so a pixel whose ||decode|| or prob
+    sits within that distance of a threshold (0.3, th_o, th_i) may flip, and `value * 255` may truncate to a neighbouring
+    uint8 level; this test bounds how far that propagates and prints the measured fractions (profiles/r02_e2e_parity.md)."""
+    import json
+    from oracle.net_oracle import NetOracle
+    from oracle.recognition_oracle import Pix2PoseOracle
+    from pix2pose_b200.recognition import pix2pose
+    w = W.synthetic_weights("resnet50", 1)
+    r = pix2pose(w, K_LM, 640, 480, OBJ, backbone="resnet50", capacity=16, max_dets=16, **TH)
+    ora = Pix2PoseOracle(NetOracle(w, "resnet50"), K_LM, 640, 480, OBJ, **TH)
+    rng = np.random.RandomState(21)
+    rois = [ROIS[0], ROIS[1], ROIS[4]]
+    for _ in range(5):
+        cy, cx, h, ww = rng.randint(100, 380), rng.randint(100, 540), rng.randint(60, 130), rng.randint(60, 130)
+        rois.append([cy - h // 2, cx - ww // 2, cy + h // 2, cx + ww // 2])
+    stats = dict(n=0, same_outcome=0, same_bbox_t=0, crops_identical=0, px=0, px_diff=0, px_diff_gt1=0, mask_px_diff=0, ang=[], dt=[], dfrac=[])
+    for roi in rois:
+        want = ora.est_pose(frame, np.array(roi))
+        got = r.est_pose(frame, np.array(roi))
+        stats["n"] += 1
+        same = isinstance(want[1], int) == isinstance(got[1], int)
+        stats["same_outcome"] += same
+        stats["same_bbox_t"] += list(want[5]) == list(got[5])
+        if not same or isinstance(want[1], int):
+            continue
+        if want[0].shape == got[0].shape:
+            d = np.abs(want[0].astype(int) - got[0].astype(int))
+            stats["crops_identical"] += int(d.max() == 0)
+            stats["px"] += d.size
+            stats["px_diff"] += int((d > 0).sum())
+            stats["px_diff_gt1"] += int((d > 1).sum())
+            stats["mask_px_diff"] += int((want[1] != got[1]).sum())
+        stats["ang"].append(float(np.degrees(np.arccos(np.clip((np.trace(want[2].T @ got[2]) - 1) / 2, -1, 1)))))
+        stats["dt"].append(float(np.linalg.norm(want[3] - got[3]) / np.linalg.norm(want[3])))
+        stats["dfrac"].append(abs(float(want[4]) - float(got[4])))
+    out = dict(stats, ang_max=max(stats["ang"], default=0), dt_max=max(stats["dt"], default=0), dfrac_max=max(stats["dfrac"], default=0))
+    with capsys.disabled():
+        print("\nE2E_PARITY " + json.dumps({k: v for k, v in out.items() if k not in ("ang", "dt", "dfrac")}))
+    assert stats["same_outcome"] == stats["n"]                       # pose / sentinel decision agrees everywhere
+    assert stats["px"] > 0
+    assert stats["px_diff_gt1"] <= 1e-3 * stats["px"]                # uint8 XYZ: at most one level off, except near gray/threshold flips
+    assert stats["px_diff"] <= 0.1 * stats["px"]
