@@ -152,6 +152,12 @@ P2P_API int p2p_pipeline_debug_override(p2p_pipeline_t* p, int stage, const floa
 /* box_size of pix2pose.__init__ (recognition.py:10, :19; used by get_boxes :33-34 for the stage-1 box and for the
  * refined boxes :110).  Applies to the following runs; default 1.5. */
 P2P_API int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size);
+/* Asynchronous use (throughput loops): after p2p_pipeline_set_async(p, 1) the p2p_pipeline_run* calls return as soon as the
+ * batch is queued on the device (their `out` argument is ignored); p2p_pipeline_wait blocks until the records of that run
+ * are on the host and copies them to `out`.  One run in flight per pipeline: alternate between two pipelines to prepare and
+ * queue batch k+1 while batch k computes (pix2pose_b200.recognition.pix2pose.est_pose_batch_async). */
+P2P_API int p2p_pipeline_set_async(p2p_pipeline_t* p, int on);
+P2P_API int p2p_pipeline_wait(p2p_pipeline_t* p, p2p_pose_t* out);
 /* Test hook: candidate selection (recognition.py:158-178, :189-193) of the last run repeated with caller-supplied PnP results
  * for its n_cands compact candidates (Rt: 12 doubles each = R row-major, t; n_inliers; status 1 = pose, 0 = inliers None). */
 P2P_API int p2p_pipeline_debug_select(p2p_pipeline_t* p, const double* Rt, const int* n_inliers, const int* status, int n_cands,

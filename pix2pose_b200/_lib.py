@@ -82,6 +82,8 @@ def lib():
         "p2p_pipeline_debug_override": (ctypes.c_int, [vp, ctypes.c_int, c_f, c_f, ctypes.c_int]),
         "p2p_pipeline_launch_count": (ctypes.c_longlong, [vp]),
         "p2p_pipeline_forward_ms": (ctypes.c_int, [vp, c_d]),
+        "p2p_pipeline_set_async": (ctypes.c_int, [vp, ctypes.c_int]),
+        "p2p_pipeline_wait": (ctypes.c_int, [vp, vp]),
         "p2p_pipeline_debug_select": (ctypes.c_int, [vp, c_d, c_i, c_i, ctypes.c_int, ctypes.c_int, vp]),
         "p2p_time_forward": (ctypes.c_int, [vp, vp, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]),
         "p2p_engine_event_record": (ctypes.c_int, [vp, ctypes.c_int]),

@@ -214,6 +214,18 @@ int p2p_pipeline_set_box_size(p2p_pipeline_t* p, double box_size) {
         p->p->box_size = box_size;
     });
 }
+int p2p_pipeline_set_async(p2p_pipeline_t* p, int on) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->async_mode = on != 0;
+    });
+}
+int p2p_pipeline_wait(p2p_pipeline_t* p, p2p_pose_t* out) {
+    return guarded([&] {
+        P2P_CHECK(p, "NULL argument");
+        p->p->wait(reinterpret_cast<PoseRecord*>(out));
+    });
+}
 int p2p_pipeline_debug_select(p2p_pipeline_t* p, const double* Rt, const int* n_inliers, const int* status, int n_cands, int n,
                               p2p_pose_t* out) {
     return guarded([&] {

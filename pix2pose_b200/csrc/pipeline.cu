@@ -583,6 +583,7 @@ Pipeline::~Pipeline() {
     if (pinned_dets_) cudaFreeHost(pinned_dets_);
     if (pinned_recs_) cudaFreeHost(pinned_recs_);
     for (auto e : fwd_ev_) cudaEventDestroy(e);
+    if (done_ev_) cudaEventDestroy(done_ev_);
     if (copy_stream_) {
         cudaStreamDestroy(copy_stream_);
         for (auto& e : frames_ready_) cudaEventDestroy(e);
@@ -671,8 +672,12 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
                    int W, const DetIn* dets, int n, const double* th_o, double th_i, float reproj_err, int iters, double confidence,
                    PoseRecord* out) {
     P2P_CHECK(n >= 0 && n <= max_dets, "run: %d detections, pipeline built for %d", n, max_dets);
-    if (n == 0) return;
-    P2P_CHECK(frames_dev && dets && out && models && seg_counts && n_seg >= 1, "NULL argument");
+    P2P_CHECK(pending_n_ < 0, "run: the previous asynchronous run of this pipeline has not been collected (p2p_pipeline_wait)");
+    if (n == 0) {
+        if (async_mode) pending_n_ = 0, (void)(done_ev_ || cudaEventCreateWithFlags(&done_ev_, cudaEventDisableTiming)), cudaEventRecord(done_ev_, engine->stream);
+        return;
+    }
+    P2P_CHECK(frames_dev && dets && (out || async_mode) && models && seg_counts && n_seg >= 1, "NULL argument");
     cudaStream_t s = engine->stream;
     host_dets_.assign(dets, dets + n);
     host_seg_.assign(2 * (n_seg + 1), 0);
@@ -780,8 +785,20 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
     if (fslot >= 0) P2P_CUDA(cudaEventRecord(frames_free_[fslot], s));
     last_n_fwd_ev_ = 4;
     P2P_CUDA(cudaMemcpyAsync(pinned_recs_, recs_.p, sizeof(PoseRecord) * n, cudaMemcpyDeviceToHost, s));
-    P2P_CUDA(cudaStreamSynchronize(s));
-    memcpy(out, pinned_recs_, sizeof(PoseRecord) * n);
+    if (!done_ev_) P2P_CUDA(cudaEventCreateWithFlags(&done_ev_, cudaEventDisableTiming));
+    P2P_CUDA(cudaEventRecord(done_ev_, s));
+    pending_n_ = n;
+    if (!async_mode) wait(out);
+}
+
+void Pipeline::wait(PoseRecord* out) {
+    // Collects the records of the run launched last (async_mode: run() returns as soon as the work is queued, so the host
+    // can prepare and queue the next batch -- on another pipeline instance -- while this one computes).
+    P2P_CHECK(pending_n_ >= 0 && done_ev_, "wait: no run in flight");
+    P2P_CHECK(out, "NULL argument");
+    P2P_CUDA(cudaEventSynchronize(done_ev_));
+    memcpy(out, pinned_recs_, sizeof(PoseRecord) * pending_n_);
+    pending_n_ = -1;
 }
 
 void Pipeline::debug_select(const double* Rt, const int* n_inliers, const int* status, int n_cands, int n, PoseRecord* out) {

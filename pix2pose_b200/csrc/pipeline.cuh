@@ -81,6 +81,9 @@ class Pipeline {
     void run(const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int F, int H,
              int W, const DetIn* dets, int n, const double* th_o, double th_i, float reproj_err, int iters, double confidence,
              PoseRecord* out);
+    // async_mode: run() returns once the work is queued (`out` unused); wait() blocks until that run's records are on the host.
+    bool async_mode = false;
+    void wait(PoseRecord* out);
     // After run(): copy the winner's uint8 XYZ crop (h,w,3) and valid mask (h,w) of detection d
     // (h = v2-v1, w = u2-u1 of best_box) into host buffers sized for cap_px pixels.
     void fetch_crop(int d, const PoseRecord& rec, uint8_t* xyz_out, uint8_t* mask_out);
@@ -137,6 +140,8 @@ class Pipeline {
     long long pool_gen_ = 0;
     std::vector<cudaEvent_t> fwd_ev_;
     int n_fwd_ev_ = 0, last_n_fwd_ev_ = 0;
+    cudaEvent_t done_ev_ = nullptr;
+    int pending_n_ = -1;
     DetIn* pinned_dets_ = nullptr;
     PoseRecord* pinned_recs_ = nullptr;
     void enqueue(int phase, const Model* const* models, const int* seg_counts, int n_seg, const void* frames_dev, bool frames_f32, int H,

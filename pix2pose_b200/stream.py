@@ -78,3 +78,108 @@ class MultiObjectRecognizer:
         rec[order, 9:12] = a["t"]
         rec[order, 12], rec[order, 13], rec[order, 14] = a["n_inliers"], a["frac_inlier"], a["status"]
         return rec, rec[:, 14].astype(np.int32)
+
+
+class AsyncBatcher:
+    """Throughput loops: batch k+1 is prepared on the host (boxes, detection records) and queued on the device while batch k
+    still computes.  Two device pipelines are used alternately (one run in flight per pipeline, ``p2p_pipeline_set_async`` /
+    ``p2p_pipeline_wait``); both share the engine's stream, so the device simply runs the batches back to back and never
+    waits for Python.  ``owner``: a ``pix2pose`` (one object) or a ``MultiObjectRecognizer`` (``submit`` then takes the
+    detections' object ids).  The synchronous ``est_pose_batch`` / ``est_pose_stream`` path is untouched."""
+
+    def __init__(self, owner, max_dets):
+        self.multi = owner if isinstance(owner, MultiObjectRecognizer) else None
+        self.first = next(iter(owner.models.values())) if self.multi else owner
+        eng = self.first.generator_train.engine
+        self.n_th = len(np.asarray(self.first.th_o).reshape(-1))
+        self.pipes = []
+        for _ in range(2):
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().p2p_pipeline_create(eng.handle, int(max_dets), self.n_th, ctypes.byref(h)))
+            _lib.check(_lib.lib().p2p_pipeline_set_async(h, 1))
+            self.pipes.append(h)
+        self.turn = 0
+        self.inflight = [None, None]
+
+    def close(self):
+        for t in (0, 1):
+            if self.inflight[t] is not None:
+                self.result(self.inflight[t])
+        for h in self.pipes:
+            _lib.lib().p2p_pipeline_destroy(h)
+        self.pipes = []
+
+    @property
+    def launch_count(self):
+        return sum(int(_lib.lib().p2p_pipeline_launch_count(h)) for h in self.pipes)
+
+    def upload_frames(self, frames):
+        """Queues the H2D copy of `frames` for the batch the NEXT ``submit`` runs (same pipeline, its copy stream)."""
+        frames = np.ascontiguousarray(np.asarray(frames, np.uint8))
+        if frames.ndim == 3:
+            frames = frames[None]
+        pipe = self.pipes[self.turn]
+        dev = ctypes.c_void_p()
+        _lib.check(_lib.lib().p2p_pipeline_upload_frames(pipe, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), frames.shape[0],
+                                                         frames.shape[1], frames.shape[2], ctypes.byref(dev)))
+        return (dev, frames.shape[0], frames.shape[1], frames.shape[2], self.turn)
+
+    def submit(self, frames_dev, rois, frame_ids, obj_ids=None):
+        """Queues one batch; returns a ticket for ``result``.  `frames_dev`: handle of ``upload_frames`` (of this batcher, or of
+        the owner for frames that stay resident)."""
+        dev, F, H, W = frames_dev[:4]
+        t = self.turn
+        if self.inflight[t] is not None:
+            raise RuntimeError("both pipelines are busy: collect a result first")
+        rois = np.asarray(rois).reshape(-1, 4)
+        frame_ids = np.asarray(frame_ids)
+        n = len(rois)
+        if self.multi is None:
+            groups = [(self.first, np.arange(n))]
+        else:
+            obj_ids = np.asarray(obj_ids)
+            groups = [(self.multi.models[o], np.nonzero(obj_ids == o)[0]) for o in np.unique(obj_ids) if o in self.multi.models]
+        n_known = int(sum(len(idx) for _, idx in groups))
+        dets = (_Det * max(n_known, 1))()
+        da = np.frombuffer(dets, dtype=DET_DTYPE, count=max(n_known, 1))
+        order, counts, handles, at = [], [], [], 0
+        for m, idx in groups:
+            part = m._make_dets((H, W), rois[idx], frame_ids[idx], None)
+            da[at:at + len(idx)] = np.frombuffer(part, dtype=DET_DTYPE, count=len(idx))
+            at += len(idx)
+            order.append(idx); counts.append(len(idx)); handles.append(m.generator_train._model)
+        poses = (_Pose * max(n_known, 1))()
+        pipe = self.pipes[t]
+        _lib.check(_lib.lib().p2p_pipeline_set_box_size(pipe, float(self.first.box_size)))
+        if n_known:
+            _lib.check(_lib.lib().p2p_pipeline_run_multi(pipe, (ctypes.c_void_p * len(handles))(*[h.value for h in handles]),
+                                                         (ctypes.c_int * len(counts))(*counts), len(counts), dev, 0, F, H, W, dets,
+                                                         n_known, 5.0, 100, 0.99, poses))
+        ticket = (t, poses, n, n_known, np.concatenate(order) if order else np.zeros(0, np.int64), dets)
+        self.inflight[t] = ticket
+        self.turn ^= 1
+        return ticket
+
+    def result(self, ticket):
+        """Blocks until the ticket's batch is done: (records (n,16) in submission order, status (n,))."""
+        t, poses, n, n_known, order, _dets = ticket
+        if self.inflight[t] is not ticket:
+            raise RuntimeError("ticket already collected")
+        if n_known:
+            _lib.check(_lib.lib().p2p_pipeline_wait(self.pipes[t], poses))
+        self.inflight[t] = None
+        rec = np.zeros((n, 16))
+        rec[:, 14] = -3
+        rec[:, 15] = np.arange(n)
+        if n_known:
+            a = np.frombuffer(poses, dtype=POSE_DTYPE, count=n_known)
+            rec[order, :9] = a["R"]
+            rec[order, 9:12] = a["t"]
+            rec[order, 12], rec[order, 13], rec[order, 14] = a["n_inliers"], a["frac_inlier"], a["status"]
+        self.last_n_cand = np.frombuffer(poses, dtype=POSE_DTYPE, count=max(n_known, 1))["n_cand"][:n_known].copy()
+        return rec, rec[:, 14].astype(np.int32)
+
+    def last_forward_ms(self, ticket_slot):
+        ms = ctypes.c_double()
+        _lib.check(_lib.lib().p2p_pipeline_forward_ms(self.pipes[ticket_slot], ctypes.byref(ms)))
+        return ms.value

@@ -68,6 +68,21 @@ class FakeRec:
 
 import pix2pose_b200.recognition as R
 R.pix2pose = FakeRec
+import pix2pose_b200.stream as S
+class FakeBatcher:
+    launch_count = 0
+    def __init__(self, owner, n): self.n, self.k = n, 0
+    def upload_frames(self, frames): return (None, 1, 480, 640, 0)
+    def submit(self, fdev, rois, fids, oids=None):
+        FakeBatcher.launch_count += 150
+        self.k += 1
+        return (self.k %% 2, len(rois))
+    def result(self, t):
+        self.last_n_cand = np.full(t[1], 3)
+        return np.zeros((t[1], 16)), np.ones(t[1], int)
+    def last_forward_ms(self, slot): return 28.0
+    def close(self): pass
+S.AsyncBatcher = FakeBatcher
 import pix2pose_b200.weights as W
 W.synthetic_weights = lambda *a, **k: {}
 

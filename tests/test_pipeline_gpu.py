@@ -460,3 +460,27 @@ def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
         print("\nE2E_PARITY " + json.dumps(st))
     assert st["same_outcome"] == st["n"]                              # pose / sentinel decision agrees everywhere
     assert st["stage1_mask_flips"] <= 2e-3 * st["stage1_px"]          # ~2e-4 network error x density of values near a threshold
+
+
+def test_async_batcher_equals_synchronous_calls(rec, frame):
+    """Two batches in flight on two alternating device pipelines (stream.AsyncBatcher) return exactly what the synchronous
+    est_pose_batch returns for the same detections, in submission order, also when the batches differ."""
+    from pix2pose_b200.stream import AsyncBatcher
+    rois_a = np.array(ROIS)
+    rois_b = np.array(ROIS[::-1][:3])
+    want_a = rec.est_pose_batch(frame, rois_a).records()
+    want_b = rec.est_pose_batch(frame, rois_b).records()
+    b = AsyncBatcher(rec, 16)
+    fdev = rec.upload_frames(frame, 16)
+    t1 = b.submit(fdev, rois_a, np.zeros(len(rois_a), int))
+    t2 = b.submit(fdev, rois_b, np.zeros(len(rois_b), int))
+    with pytest.raises(RuntimeError):
+        b.submit(fdev, rois_a, np.zeros(len(rois_a), int))           # both pipelines busy
+    r1, s1 = b.result(t1)
+    t3 = b.submit(b.upload_frames(frame), rois_a, np.zeros(len(rois_a), int))   # per-batch upload on the batcher's own copy stream
+    r2, s2 = b.result(t2)
+    r3, s3 = b.result(t3)
+    for got, want in ((r1, want_a), (r2, want_b), (r3, want_a)):
+        assert np.array_equal(got[:, :15], want[:, :15])
+    assert b.last_forward_ms(t3[0]) > 0
+    b.close()
