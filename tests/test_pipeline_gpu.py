@@ -405,12 +405,10 @@ def test_candidate_selection_fed_with_cv2_results(rec, frame, seed, roi, rv, t):
 def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
     """Oracle generator (torch-CPU fp32) -> oracle pipeline against GPU generator -> GPU pipeline, on REAL network outputs
     (VERDICT r1, weak #3).  The two generators agree to ~2e-4 (tests/test_net_gpu.py), so a pixel whose ||decode|| or prob
-    sits within that distance of a threshold (0.3, th_o, th_i) may flip.  On this fixture (RANDOM weights: noise-like maps,
-    a large share of pixels near every threshold) one flipped stage-1 pixel can move the integer mask centroid / bounding box
-    (:101-109) and with it the refined crop by a pixel, after which the stage-2 inputs are different images; a trained
-    network's smooth maps do not behave like that.  So the test asserts what must hold regardless -- the pose / sentinel
-    decision of every detection, and, for detections whose crop geometry came out the same, uint8 XYZ maps that differ by at
-    most one level almost everywhere -- and prints the measured fractions (profiles/r02_e2e_parity.md)."""
+    sits within that distance of a threshold (0.3, th_o, th_i) may flip, and `value * 255` may truncate to the neighbouring
+    uint8 level.  The test bounds how far that propagates -- same pose / sentinel decision for every detection, a handful of
+    flipped stage-1 mask pixels, and for the detections that return the same pose, uint8 XYZ crops that differ by at most
+    one level in at most 1 % of the pixels -- and prints the measured fractions (profiles/r02_e2e_parity.md)."""
     import json
     from oracle.net_oracle import NetOracle
     from oracle.recognition_oracle import Pix2PoseOracle
@@ -423,7 +421,7 @@ def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
     for _ in range(9):
         cy, cx, h, ww = rng.randint(100, 380), rng.randint(100, 540), rng.randint(60, 130), rng.randint(60, 130)
         rois.append([cy - h // 2, cx - ww // 2, cy + h // 2, cx + ww // 2])
-    st = dict(n=0, same_outcome=0, same_bbox_t=0, same_geometry=0, crops_identical=0, px=0, px_diff=0, px_diff_gt1=0, mask_px_diff=0,
+    st = dict(n=0, same_outcome=0, same_bbox_t=0, same_geometry=0, same_pose=0, crops_identical=0, px=0, px_diff=0, px_diff_gt1=0, mask_px_diff=0,
               stage1_px=0, stage1_mask_flips=0)
     ang, dt = [], []
     for roi in rois:
@@ -448,6 +446,8 @@ def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
         dt.append(float(np.linalg.norm(want[3] - got[3]) / np.linalg.norm(want[3])))
         if list(want[5]) == list(got[5]) and want[0].shape == got[0].shape:
             st["same_geometry"] += 1
+        if ang[-1] <= 1e-5 and dt[-1] <= 1e-9 and want[0].shape == got[0].shape:      # same winner, same consensus set
+            st["same_pose"] += 1
             d = np.abs(want[0].astype(int) - got[0].astype(int))
             st["crops_identical"] += int(d.max() == 0)
             st["px"] += d.size
@@ -460,6 +460,11 @@ def test_end_to_end_cpu_oracle_vs_gpu_on_real_network_outputs(frame, capsys):
         print("\nE2E_PARITY " + json.dumps(st))
     assert st["same_outcome"] == st["n"]                              # pose / sentinel decision agrees everywhere
     assert st["stage1_mask_flips"] <= 2e-3 * st["stage1_px"]          # ~2e-4 network error x density of values near a threshold
+    # measured (profiles/r02_e2e_parity.md): 11 of 12 detections return the SAME pose to 1e-14 (same winning candidate, same
+    # RANSAC consensus set) and uint8 XYZ crops that differ in ~0.1 % of the pixels, by one level; the twelfth picks another
+    # candidate (on noise-like maps PnP poses are near-random and a single flipped correspondence changes the consensus)
+    assert st["same_pose"] >= 0.75 * st["pose_pairs"]
+    assert st["px_diff_gt1"] == 0 and st["px_diff"] <= 0.01 * st["px"]
 
 
 def test_async_batcher_equals_synchronous_calls(rec, frame):
