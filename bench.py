@@ -461,7 +461,7 @@ def run_ours(args):
         state["all"] = gather.result()
         gather.submit(r, gidx)
 
-    ms_e2e, _ = timed(step_e2e, args.steps, 3, eng)
+    ms_e2e, _ = timed(step_e2e, args.steps, 5, eng)     # 5 warm-ups: two frame buffers alternate, each configuration runs plain once, then is captured
     h2d = int(frames.nbytes + n_det * ctypes.sizeof(_Det) + 64)
     d2h = int(n_det * ctypes.sizeof(_Pose))
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv), measured live on the real step

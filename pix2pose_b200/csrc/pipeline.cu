@@ -735,7 +735,12 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
             key.push_back(seg_counts[sg]);
         }
         auto it = graphs_.find(key);
-        if (it == graphs_.end()) {
+        if (it == graphs_.end() && seen_keys_.insert(key).second) {
+            // first run of this configuration: launch kernel by kernel.  Capturing and instantiating five graphs costs about
+            // as much as two plain runs' worth of launches, which only pays off when the configuration comes back (throughput
+            // loops do; the per-image evaluation loop, where the detection count changes from image to image, mostly does not)
+            if (seen_keys_.size() > 4096) seen_keys_.clear();
+        } else if (it == graphs_.end()) {
             if (graphs_.size() >= 32) {   // bounded cache: drop everything rather than track recency
                 for (auto& g : graphs_)
                     for (auto& e : g.second.exec) cudaGraphExecDestroy(e);
@@ -767,7 +772,7 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
         } else {
             launches += it->second.launches;   // the counters only saw these kernels while they were captured
         }
-        ge = &it->second;
+        if (it != graphs_.end()) ge = &it->second;
     }
     if (fwd_ev_.empty()) {
         fwd_ev_.resize(4);

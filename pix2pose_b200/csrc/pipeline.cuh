@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <set>
 #include <vector>
 
 #include "common.cuh"
@@ -137,6 +138,7 @@ class Pipeline {
     // into CUDA graphs (one per phase, see enqueue) per configuration and replayed: ~150 launches cost five graph launches.
     struct GraphEntry { cudaGraphExec_t exec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; long long launches = 0; };
     std::map<std::vector<long long>, GraphEntry> graphs_;
+    std::set<std::vector<long long>> seen_keys_;   // configurations run once so far (captured on their second appearance)
     long long pool_gen_ = 0;
     std::vector<cudaEvent_t> fwd_ev_;
     int n_fwd_ev_ = 0, last_n_fwd_ev_ = 0;
