@@ -10,7 +10,10 @@
 // published algorithm of modules/calib3d/src/epnp.cpp: control points from PCA, barycentric
 // coordinates, M^T M null space, three beta approximations (N = 4 / 2 / 3 linearisations), five
 // Gauss-Newton steps each, Horn-style R|t from the SVD of the 3x3 correlation, best reprojection
-// error wins.
+// error wins -- and, because the 5-point case depends on every rounding of it, OpenCV's linear algebra
+// (Jacobi SVD, SVD back-substitution, mulTransposed) operation by operation; both are pinned against the
+// image's cv2 by tests/test_epnp_host.py (bitwise).  Compile WITHOUT mul+add contraction (-fmad=false /
+// -ffp-contract=off): an FMA where OpenCV has a separate multiply and add changes the result.
 #pragma once
 #include <math.h>
 
@@ -31,12 +34,12 @@ P2P_HD inline double dist2(const double* a, const double* b) {
 }
 
 // Symmetric eigen-decomposition by Householder tridiagonalisation + implicit-shift QL (the classic
-// tred2 / tqli pair): ~10x fewer operations than cyclic Jacobi for N = 12, which matters because the RANSAC
-// kernel runs one of these per hypothesis per thread.  Same contract as jacobi_eig_sym: `A` (row-major) is
-// destroyed, w descending, row i of `Vt` = unit eigenvector of w[i].
-// FIRST > 0 keeps only the eigenvectors FIRST .. N-1 (the smallest eigenvalues): row i of the full Vt lands in row
-// i - FIRST of `Vt` ((N - FIRST) x N).  EPnP only ever reads the last four, and the RANSAC kernel is bound by the
-// per-thread local-memory footprint, so the 5-point solver does not materialise the other eight.
+// tred2 / tqli pair): ~10x fewer operations than cyclic Jacobi for N = 12.  Used by the LARGE-n refit only (one per
+// problem, serial tail of epnp_refit_kernel): for n >= 6 noisy points the four smallest eigenvalues of M^T M are well
+// separated and any accurate solver agrees with OpenCV's Jacobi to ~1e-13; the 5-point hypotheses and the refits on small
+// consensus sets need OpenCV's exact Jacobi (cv_jacobi_svd12_ut below).  `A` (row-major, symmetric) is destroyed, w
+// descending, row i of `Vt` = unit eigenvector of w[i].  FIRST > 0 keeps only the eigenvectors FIRST .. N-1 (the
+// smallest eigenvalues): row i of the full Vt lands in row i - FIRST of `Vt` ((N - FIRST) x N); EPnP reads the last four.
 template <int N, int FIRST = 0>
 P2P_HD inline void tridiag_eig_sym(double* A, double* Vt, double* w) {
     double d[N], e[N];
@@ -557,14 +560,6 @@ P2P_HD inline void barycentric(const double* ci, const double cws[4][3], const d
     for (int j = 0; j < 3; ++j)
         a[1 + j] = ci[3 * j] * (p[0] - cws[0][0]) + ci[3 * j + 1] * (p[1] - cws[0][1]) + ci[3 * j + 2] * (p[2] - cws[0][2]);
     a[0] = 1.0 - a[1] - a[2] - a[3];
-}
-
-// The two rows fill_M writes for one correspondence.
-P2P_HD inline void m_rows(const double* a, double u, double v, const Cam& cam, double* m1, double* m2) {
-    for (int i = 0; i < 4; ++i) {
-        m1[3 * i] = a[i] * cam.fu; m1[3 * i + 1] = 0.0;           m1[3 * i + 2] = a[i] * (cam.uc - u);
-        m2[3 * i] = 0.0;           m2[3 * i + 1] = a[i] * cam.fv; m2[3 * i + 2] = a[i] * (cam.vc - v);
-    }
 }
 
 // ut8 = rows 8..11 of the 12 x 12 eigenvector matrix (4 x 12): the null-space candidates, smallest eigenvalue last.

@@ -33,16 +33,16 @@ __device__ __forceinline__ float reproj_err_f32(const double* R, const double* t
 
 // Inlier test for the scoring kernel: the same decision as reproj_err_f32(...) <= thr2, but evaluated in fp32 first;
 // only correspondences whose fp32 error lands within `margin` of the threshold (fp32 error bound ~1e-3 px^2 at
-// 5 px) or is not finite are re-evaluated through the exact fp64 path.  Rf/tf are float copies of R/t.
-__device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t, const float* Rf, const float* tf, const float* o,
-                                               const float* ip, const PnpProblem& pr, float fuf, float fvf, float ucf, float vcf,
-                                               float thr2) {
+// 5 px) or is not finite are re-evaluated through the exact fp64 path.  Pf = float copy of the projection matrix
+// K [R|t] (rows 0-1 scaled by fu / fv, so no separate intrinsics multiply), row 2 = the depth.
+__device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t, const float* Pf, const float* o,
+                                               const float* ip, const PnpProblem& pr, float ucf, float vcf, float thr2) {
     const float X = o[0], Y = o[1], Z = o[2];
-    const float x = fmaf(Rf[0], X, fmaf(Rf[1], Y, fmaf(Rf[2], Z, tf[0])));
-    const float y = fmaf(Rf[3], X, fmaf(Rf[4], Y, fmaf(Rf[5], Z, tf[1])));
-    const float z = fmaf(Rf[6], X, fmaf(Rf[7], Y, fmaf(Rf[8], Z, tf[2])));
-    const float iz = __frcp_rn(z);
-    const float dx = ip[0] - fmaf(x * iz, fuf, ucf), dy = ip[1] - fmaf(y * iz, fvf, vcf);
+    const float x = fmaf(Pf[0], X, fmaf(Pf[1], Y, fmaf(Pf[2], Z, Pf[3])));
+    const float y = fmaf(Pf[4], X, fmaf(Pf[5], Y, fmaf(Pf[6], Z, Pf[7])));
+    const float z = fmaf(Pf[8], X, fmaf(Pf[9], Y, fmaf(Pf[10], Z, Pf[11])));
+    const float iz = __fdividef(1.0f, z);                       // approximate reciprocal: the margin below absorbs its error
+    const float dx = (ip[0] - ucf) - x * iz, dy = (ip[1] - vcf) - y * iz;
     const float e = fmaf(dx, dx, dy * dy);
     const float margin = 0.01f * thr2 + 0.05f;
     if (fabsf(e - thr2) > margin && fabsf(z) > 1e-3f) return e <= thr2;   // NaN/inf fall through to the exact path
@@ -118,18 +118,25 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
     for (int i = threadIdx.x; i < cnt_pts * 2; i += blockDim.x) s_ip[i] = gi[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float fuf = static_cast<float>(pr.fu), fvf = static_cast<float>(pr.fv), ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
+    const float ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
     for (int h = warp; h < iters; h += kScoreWarps) {
         const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
         double R[9], t[3];
-        float Rf[9], tf[3];
+        float Pf[12];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { R[i] = m[i]; Rf[i] = static_cast<float>(R[i]); }
+        for (int i = 0; i < 9; ++i) R[i] = m[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { t[i] = m[9 + i]; tf[i] = static_cast<float>(t[i]); }
+        for (int i = 0; i < 3; ++i) t[i] = m[9 + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Pf[i] = static_cast<float>(R[i] * pr.fu);
+            Pf[4 + i] = static_cast<float>(R[3 + i] * pr.fv);
+            Pf[8 + i] = static_cast<float>(R[6 + i]);
+        }
+        Pf[3] = static_cast<float>(t[0] * pr.fu); Pf[7] = static_cast<float>(t[1] * pr.fv); Pf[11] = static_cast<float>(t[2]);
         int cnt = 0;
         for (int i = lane; i < cnt_pts; i += 32)
-            cnt += is_inlier_fast(R, t, Rf, tf, s_o + 3 * i, s_ip + 2 * i, pr, fuf, fvf, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
+            cnt += is_inlier_fast(R, t, Pf, s_o + 3 * i, s_ip + 2 * i, pr, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0 && cnt) atomicAdd(&counts[blockIdx.y * iters + h], cnt);
