@@ -638,7 +638,12 @@ Engine::~Engine() {
 
 // ------------------------------------------------------------------------------------------------
 // model = packed weights for one object
-Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng) {
+static long long next_model_id() {
+    static long long n = 0;
+    return ++n;
+}
+
+Model::Model(Engine* eng, const float* blob, size_t n_floats) : engine(eng), id(next_model_id()) {
     const std::vector<LayerDef> L = layer_table(eng->backbone);
     const size_t want = param_count(eng->backbone);
     P2P_CHECK(n_floats == want, "weight blob has %zu floats, backbone needs %zu", n_floats, want);

@@ -88,6 +88,7 @@ class Model {
     Model(Engine* eng, const float* blob, size_t n_floats);
     std::vector<ModelConv> convs;
     Engine* engine;
+    long long id;   // unique per process (keys of the captured graphs)
 };
 
 class Engine {

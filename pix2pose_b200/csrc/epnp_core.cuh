@@ -660,14 +660,6 @@ P2P_HD inline void betas_from_ut(const double* ut8, const double cws[4][3], doub
     find_betas_approx_3<S>(l, rho, betas[2], ws); gauss_newton<S>(l, rho, betas[2]);
 }
 
-// Large-n refit path: the eigenvectors of the four smallest eigenvalues of M^T M by tridiagonal QL (for n >= 6 noisy
-// points they are well separated, so any accurate eigen-solver agrees with cv2 to ~1e-13; signs cancel in the betas).
-P2P_HD inline void solve_betas(double* mtm, const double cws[4][3], double* ut8, double betas[3][4]) {
-    double w[12], lws[60 + kWs];
-    tridiag_eig_sym<12, 8>(mtm, ut8, w);
-    betas_from_ut<1>(ut8, cws, betas, lws);
-}
-
 // Small-n path, bit-exact: cvSVD(MtM, D, Ut, 0, CV_SVD_MODIFY_A | CV_SVD_U_T) in place on `mtm` (144 doubles, element
 // stride S); rows 8..11 are copied out and the storage is then reused as the L_6x10 / SVD scratch.
 template <int S = 1>
@@ -796,10 +788,17 @@ P2P_HD inline void rodrigues_to_mat(const double* r, double R[3][3]) {
 // block reduction --
 //   s[k], s[10+k], s[20+k], s[30+k], k = pair (x <= y) of control points: sum of a_x a_y {1, du, dv, du^2 + dv^2}
 //   (du = uc - u, dv = vc - v): M^T M in structured form;   s[40 + 3j + c] = sum a_j (pw_c - c0_c): correlation terms.
-// This serial tail turns them into the three candidate poses.  pf = first inlier (solve_for_sign looks at point 0).
-P2P_HD inline void refit_candidates(const double* s, int m, const double* c0, const double cws[4][3], const double* ci, const Cam& cam,
-                                    const double* pf, double Rs[3][3][3], double ts[3][3]) {
-    double mtm[144], ut[48], betas[3][4];
+// The serial tail turns them into the three candidate poses in two steps: refit_prepare (one thread: eigenvectors, L_6x10,
+// rho and the sums every candidate shares) and refit_candidate (independent per candidate c = 0, 1, 2: beta initialisation
+// c, Gauss-Newton, R|t -- three threads of the block run them side by side).  pf = first inlier (solve_for_sign looks at
+// point 0).
+struct RefitShared {
+    double ut8[48], l[60], rho[6], af[4], Srow[4], dsum[3];
+};
+
+P2P_HD inline void refit_prepare(const double* s, const double cws[4][3], const double* ci, const Cam& cam, const double* pf,
+                                 RefitShared& sh) {
+    double mtm[144], w[12];
     int k = 0;
     for (int x = 0; x < 4; ++x)
         for (int y = x; y < 4; ++y) {
@@ -812,40 +811,47 @@ P2P_HD inline void refit_candidates(const double* s, int m, const double* c0, co
                 }
             ++k;
         }
-    solve_betas(mtm, cws, ut, betas);
-    double af[4];
-    barycentric(ci, cws, pf, af);
+    // the eigenvectors of the four smallest eigenvalues of M^T M by tridiagonal QL (see tridiag_eig_sym)
+    tridiag_eig_sym<12, 8>(mtm, sh.ut8, w);
+    compute_L_6x10<1>(sh.ut8, sh.l);
+    compute_rho(cws, sh.rho);
+    barycentric(ci, cws, pf, sh.af);
     // S_j = sum_i alpha_ij: alpha sums to 1 per point, so it is the row sum of the pair table
-    double Srow[4] = {0, 0, 0, 0};
+    for (int j = 0; j < 4; ++j) sh.Srow[j] = 0;
     k = 0;
     for (int x = 0; x < 4; ++x)
         for (int y = x; y < 4; ++y) {
-            Srow[x] += s[k];
-            if (y != x) Srow[y] += s[k];
+            sh.Srow[x] += s[k];
+            if (y != x) sh.Srow[y] += s[k];
             ++k;
         }
-    double dsum[3] = {0, 0, 0};   // sum (pw - c0): ~0 (rounding only), kept for fidelity
+    for (int q = 0; q < 3; ++q) sh.dsum[q] = 0;   // sum (pw - c0): ~0 (rounding only), kept for fidelity
     for (int j = 0; j < 4; ++j)
-        for (int q = 0; q < 3; ++q) dsum[q] += s[40 + j * 3 + q];
-    for (int c = 0; c < 3; ++c) {
-        double ccs[4][3], pc[3];
-        compute_ccs(betas[c], ut, ccs);
-        camera_point(af, ccs, pc);
-        const double sg = pc[2] < 0.0 ? -1.0 : 1.0;
-        // alphas are affine in pw:  pc0 = sum_j (S_j / m) ccs_j,  pw0 = c0,  ABt = sum_j ccs_j T_j^T - pc0 (x) sum(pw - c0)
-        double pc0[3] = {0, 0, 0}, abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < 4; ++j)
-            for (int r = 0; r < 3; ++r) ccs[j][r] *= sg;
-        for (int j = 0; j < 4; ++j)
-            for (int r = 0; r < 3; ++r) pc0[r] += Srow[j] / m * ccs[j][r];
-        for (int j = 0; j < 4; ++j)
-            for (int r = 0; r < 3; ++r)
-                for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s[40 + j * 3 + q];
+        for (int q = 0; q < 3; ++q) sh.dsum[q] += s[40 + j * 3 + q];
+}
+
+P2P_HD inline void refit_candidate(int c, const double* s, int m, const double* c0, const RefitShared& sh, double R[3][3], double* t) {
+    double betas[4], ws[kWs];
+    if (c == 0) find_betas_approx_1<1>(sh.l, sh.rho, betas, ws);
+    else if (c == 1) find_betas_approx_2<1>(sh.l, sh.rho, betas, ws);
+    else find_betas_approx_3<1>(sh.l, sh.rho, betas, ws);
+    gauss_newton<1>(sh.l, sh.rho, betas);
+    double ccs[4][3], pc[3];
+    compute_ccs(betas, sh.ut8, ccs);
+    camera_point(sh.af, ccs, pc);
+    const double sg = pc[2] < 0.0 ? -1.0 : 1.0;
+    // alphas are affine in pw:  pc0 = sum_j (S_j / m) ccs_j,  pw0 = c0,  ABt = sum_j ccs_j T_j^T - pc0 (x) sum(pw - c0)
+    double pc0[3] = {0, 0, 0}, abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 3; ++r) ccs[j][r] *= sg;
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 3; ++r) pc0[r] += sh.Srow[j] / m * ccs[j][r];
+    for (int j = 0; j < 4; ++j)
         for (int r = 0; r < 3; ++r)
-            for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * dsum[q];
-        double ws[kWs];
-        rt_from_correlation<1>(abt, pc0, c0, Rs[c], ts[c], ws);
-    }
+            for (int q = 0; q < 3; ++q) abt[3 * r + q] += ccs[j][r] * s[40 + j * 3 + q];
+    for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) abt[3 * r + q] -= pc0[r] * sh.dsum[q];
+    rt_from_correlation<1>(abt, pc0, c0, R, t, ws);
 }
 
 // Whole EPnP for a small point set held by one thread (the 5-point RANSAC hypotheses, and refits on <= MAXN inliers),

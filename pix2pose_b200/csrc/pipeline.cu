@@ -674,7 +674,11 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
     P2P_CHECK(n >= 0 && n <= max_dets, "run: %d detections, pipeline built for %d", n, max_dets);
     P2P_CHECK(pending_n_ < 0, "run: the previous asynchronous run of this pipeline has not been collected (p2p_pipeline_wait)");
     if (n == 0) {
-        if (async_mode) pending_n_ = 0, (void)(done_ev_ || cudaEventCreateWithFlags(&done_ev_, cudaEventDisableTiming)), cudaEventRecord(done_ev_, engine->stream);
+        if (async_mode) {   // an empty batch still has to be collectable
+            if (!done_ev_) P2P_CUDA(cudaEventCreateWithFlags(&done_ev_, cudaEventDisableTiming));
+            P2P_CUDA(cudaEventRecord(done_ev_, engine->stream));
+            pending_n_ = 0;
+        }
         return;
     }
     P2P_CHECK(frames_dev && dets && (out || async_mode) && models && seg_counts && n_seg >= 1, "NULL argument");
@@ -731,7 +735,7 @@ void Pipeline::run(const Model* const* models, const int* seg_counts, int n_seg,
                                       static_cast<long long>(reproj_err * 4096.0), static_cast<long long>(confidence * 1e9),
                                       static_cast<long long>(box_size * 1e6), pool_gen_, (max_cap + 2047) / 2048};
         for (int sg = 0; sg < n_seg; ++sg) {
-            key.push_back(reinterpret_cast<long long>(models[sg]));
+            key.push_back(models[sg]->id);   // not the address: a new model may be allocated where a destroyed one lived
             key.push_back(seg_counts[sg]);
         }
         auto it = graphs_.find(key);

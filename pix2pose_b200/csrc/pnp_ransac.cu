@@ -375,12 +375,16 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
             }
         block_reduce<52>(v, s_red, s_sum);
     }
+    __shared__ epnp::RefitShared s_sh;
     if (threadIdx.x == 0) {
         // sign reference: camera-frame z of the first inlier (epnp.cpp solve_for_sign uses pcs[2])
         const int f = s_first;
         const double pf[3] = {o[3 * f], o[3 * f + 1], o[3 * f + 2]};
-        epnp::refit_candidates(s_sum, m, c0, s_cws, s_ci, cam, pf, s_R, s_t);
+        epnp::refit_prepare(s_sum, s_cws, s_ci, cam, pf, s_sh);
     }
+    __syncthreads();
+    if (threadIdx.x < 3)   // the three beta initialisations are independent: one thread each instead of one after the other
+        epnp::refit_candidate(static_cast<int>(threadIdx.x), s_sum, m, c0, s_sh, s_R[threadIdx.x], s_t[threadIdx.x]);
     __syncthreads();
     // pass E: mean reprojection distance of each of the three candidates
     {

@@ -109,6 +109,12 @@ class AsyncBatcher:
             _lib.lib().p2p_pipeline_destroy(h)
         self.pipes = []
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     @property
     def launch_count(self):
         return sum(int(_lib.lib().p2p_pipeline_launch_count(h)) for h in self.pipes)

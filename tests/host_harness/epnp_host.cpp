@@ -98,7 +98,9 @@ void host_refit_large(const double* pws, const double* us, int n, const double* 
             for (int c = 0; c < 3; ++c) s[40 + j * 3 + c] += a[j] * (pws[3 * i + c] - c0[c]);
     }
     double Rs[3][3][3], ts[3][3], err[3] = {0, 0, 0};
-    epnp::refit_candidates(s, n, c0, cws, ci, cam, pws, Rs, ts);
+    epnp::RefitShared sh;
+    epnp::refit_prepare(s, cws, ci, cam, pws, sh);
+    for (int c = 0; c < 3; ++c) epnp::refit_candidate(c, s, n, c0, sh, Rs[c], ts[c]);
     for (int i = 0; i < n; ++i)
         for (int c = 0; c < 3; ++c) err[c] += epnp::reproj_dist(Rs[c], ts[c], pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
     int N = 0;
