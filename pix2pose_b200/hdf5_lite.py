@@ -93,8 +93,13 @@ class File(Group):
         Group.__init__(self, self, "/")
         self._cache = {}
         b = self._buf
-        if len(b) < 96 or b[:8] != SIGNATURE:
-            raise Hdf5Error("%s: not an HDF5 file (signature at offset 0 missing; user blocks are not supported)" % path)
+        # the superblock sits at offset 0 or, after a user block, at 512, 1024, 2048, ... (HDF5 spec II.A)
+        sb = 0
+        while not (len(b) >= sb + 96 and b[sb:sb + 8] == SIGNATURE):
+            sb = 512 if sb == 0 else sb * 2
+            if sb + 96 > len(b):
+                raise Hdf5Error("%s: not an HDF5 file (no superblock signature at offset 0, 512, 1024, ...)" % path)
+        b = b[sb:]
         ver = b[8]
         if ver in (0, 1):
             so, sl = b[13], b[14]

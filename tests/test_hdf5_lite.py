@@ -1,11 +1,33 @@
-"""Keras-HDF5 weight import without h5py: the built-in reader against files produced by the
-built-in writer (self-consistent pin: no libhdf5-written file exists in this sandbox), and the layer matching of
+"""Keras-HDF5 weight import without h5py: the built-in reader against the one libhdf5-written file
+this sandbox holds (a MATLAB 7.4 HDF5 file from scipy's test data, tests/golden/libhdf5_matlab74_testdouble.mat), against
+files produced by the built-in writer (self-consistent), and the layer matching of
 ``weights.keras_layers_to_weights`` against a file laid out the way Keras 2.2 writes the resnet50 generator
 (nested ResNet model in graph-depth order, auto-named decoder layers)."""
 import numpy as np
 import pytest
 
 from pix2pose_b200 import hdf5_lite, weights as W
+
+
+def test_reader_against_a_file_written_by_the_real_hdf5_library():
+    """tests/golden/libhdf5_matlab74_testdouble.mat is scipy/io/matlab/tests/data/testhdf5_7.4_GLNX86.mat (BSD-3, SciPy
+    developers): written in 2008 by MATLAB 7.4 through the HDF5 library itself -- 512-byte user block, version-0
+    superblock with base address 512, symbol-table root group (v1 B-tree + local heap), version-1 object header,
+    contiguous float64 dataset, fixed-length string attribute: the same structures h5py/Keras 2.2 write with
+    libver='earliest'.  scipy's own test expects testdouble = linspace(0, 2 pi, 9)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "libhdf5_matlab74_testdouble.mat")
+    raw = open(path, "rb").read()
+    assert raw[:19] == b"MATLAB 7.0 MAT-file" and raw[512:520] == hdf5_lite.SIGNATURE   # not our writer's output
+    with hdf5_lite.File(path) as f:
+        assert list(f.keys()) == ["testdouble"]
+        ds = f["testdouble"]
+        assert ds.shape == (9, 1) and ds.dtype == np.dtype("<f8")
+        assert ds.attrs["MATLAB_class"] == b"double"
+        v = np.asarray(ds)
+    np.testing.assert_allclose(v[:, 0], np.linspace(0, 2 * np.pi, 9), rtol=0, atol=1e-15)
+    # the values are the file's bytes, not a re-computation: they sit contiguously where the layout message points
+    assert raw.find(v.astype("<f8").tobytes()) >= 512
 
 
 def test_reader_roundtrip_of_groups_datasets_attributes(tmp_path):
