@@ -55,11 +55,14 @@ __device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t,
 // used to spill into 3.4 KB of local memory per thread).
 __global__ void __launch_bounds__(kHypThreads, 1) ransac_hyp_kernel(const PnpProblem* __restrict__ probs, int n_problems,
                                                                  const float* __restrict__ obj, const float* __restrict__ img,
-                                                                 double* __restrict__ hyp, int iters) {
+                                                                 double* __restrict__ hyp, int iters, int it0, int it1,
+                                                                 const uint8_t* __restrict__ done) {
     extern __shared__ double s_ws[];   // [144][kHypThreads]
-    const long long g = static_cast<long long>(blockIdx.x) * kHypThreads + threadIdx.x;
-    const int p = static_cast<int>(g / iters), h = static_cast<int>(g % iters);
+    const long long gw = static_cast<long long>(blockIdx.x) * kHypThreads + threadIdx.x;   // flat over (problem, iteration of the wave)
+    const int p = static_cast<int>(gw / (it1 - it0)), h = it0 + static_cast<int>(gw % (it1 - it0));
     if (p >= n_problems) return;
+    if (done && done[p]) return;       // OpenCV's loop ended in an earlier wave: it never draws this subset
+    const long long g = static_cast<long long>(p) * iters + h;
     const PnpProblem pr = probs[p];
     if (pr.n < 6) return;
     int idx[5];
@@ -105,12 +108,14 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
                                                                        const float* __restrict__ obj,
                                                                        const float* __restrict__ img,
                                                                        const double* __restrict__ hyp, int* __restrict__ counts,
-                                                                       int iters, float thr2) {
+                                                                       int iters, int it0, int it1, const uint8_t* __restrict__ done,
+                                                                       float thr2) {
     __shared__ float s_o[kScoreTile * 3];
     __shared__ float s_ip[kScoreTile * 2];
     const PnpProblem pr = probs[blockIdx.y];
     const int base = blockIdx.x * kScoreTile;
     if (pr.n < 6 || base >= pr.n) return;
+    if (done && done[blockIdx.y]) return;
     const int cnt_pts = min(kScoreTile, pr.n - base);
     const float* go = obj + (pr.offset + base) * 3;
     const float* gi = img + (pr.offset + base) * 2;
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
-    for (int h = warp; h < iters; h += kScoreWarps) {
+    for (int h = it0 + warp; h < it1; h += kScoreWarps) {
         const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
         double R[9], t[3];
         float Pf[12];
@@ -141,6 +146,26 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0 && cnt) atomicAdd(&counts[blockIdx.y * iters + h], cnt);
     }
+}
+
+// ---- (2b) between waves: has OpenCV's loop already ended?  The accept / adaptive-termination rule of
+// RANSACPointSetRegistrator::run replayed over the iterations scored so far; done[p] = 1 when `niters` fell to or below
+// the wave's end, i.e. the hypotheses of the later waves are ones OpenCV would never have generated.
+__global__ void ransac_wave_check_kernel(const PnpProblem* __restrict__ probs, int n_problems, const int* __restrict__ counts,
+                                         uint8_t* __restrict__ done, int iters, int wave_end, double confidence) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_problems) return;
+    const PnpProblem pr = probs[p];
+    if (pr.n < 6) { done[p] = 1; return; }
+    int max_good = 0, niters = iters > 1 ? iters : 1;
+    for (int it = 0; it < niters && it < wave_end; ++it) {
+        const int c = counts[p * iters + it];
+        if (c > (max_good > 4 ? max_good : 4)) {
+            max_good = c;
+            niters = ransac_update_num_iters(confidence, static_cast<double>(pr.n - c) / pr.n, 5, niters);
+        }
+    }
+    done[p] = niters <= wave_end ? 1 : 0;
 }
 
 // ---- (3) replay of RANSACPointSetRegistrator::run's accept / adaptive-termination rule + inlier mask
@@ -433,6 +458,7 @@ void PnpSolver::ensure(int n_problems, int iters) {
         counts_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_);
         best_.alloc(static_cast<size_t>(cap_problems_) * 2);
         small_.alloc(static_cast<size_t>(cap_problems_) * kSmallRefit);
+        done_.alloc(static_cast<size_t>(cap_problems_));
     }
 }
 
@@ -452,19 +478,32 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         P2P_CUDA(cudaEventRecord(ev[i], s));
     };
     mark(0);
-    {
-        const size_t hyp_smem = sizeof(double) * 144 * kHypThreads;
-        const long long total = static_cast<long long>(n_problems) * iters;
-        ransac_hyp_kernel<<<static_cast<unsigned>((total + kHypThreads - 1) / kHypThreads), kHypThreads, hyp_smem, s>>>(
-            problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters);
-    }
-    P2P_CUDA(cudaGetLastError());
-    mark(1);
     P2P_CHECK(max_n >= 0, "max_n must be the largest correspondence count of the batch");
     P2P_CUDA(cudaMemsetAsync(counts_.p, 0, sizeof(int) * static_cast<size_t>(n_problems) * iters, s));
-    dim3 g(std::max(1, (max_n + kScoreTile - 1) / kScoreTile), n_problems);
-    ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, thr2);
-    P2P_CUDA(cudaGetLastError());
+    // Waves in iteration order: hypotheses [0, kFirstWave) are generated and scored first; a problem whose replayed loop
+    // has ended by then (niters <= kFirstWave: a consensus of 67 % inliers or more) skips the rest, as OpenCV does.
+    static const int first_wave = getenv("P2P_RANSAC_WAVE") ? atoi(getenv("P2P_RANSAC_WAVE")) : kFirstWave;
+    const int w1 = (first_wave > 0 && iters > first_wave + first_wave / 2) ? first_wave : iters;
+    const size_t hyp_smem = sizeof(double) * 144 * kHypThreads;
+    const dim3 g(std::max(1, (max_n + kScoreTile - 1) / kScoreTile), n_problems);
+    for (int it0 = 0; it0 < iters; it0 = (it0 == 0 ? w1 : iters)) {
+        const int it1 = it0 == 0 ? w1 : iters;
+        const uint8_t* done = it0 == 0 ? nullptr : done_.p;
+        const long long total = static_cast<long long>(n_problems) * (it1 - it0);
+        ransac_hyp_kernel<<<static_cast<unsigned>((total + kHypThreads - 1) / kHypThreads), kHypThreads, hyp_smem, s>>>(
+            problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters, it0, it1, done);
+        P2P_CUDA(cudaGetLastError());
+        ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, it0, it1, done, thr2);
+        P2P_CUDA(cudaGetLastError());
+        launches += 2;
+        if (it1 < iters) {
+            ransac_wave_check_kernel<<<(n_problems + 127) / 128, 128, 0, s>>>(problems_dev, n_problems, counts_.p, done_.p, iters, it1, confidence);
+            P2P_CUDA(cudaGetLastError());
+            ++launches;
+            mark(1);
+        }
+    }
+    if (w1 == iters) mark(1);
     mark(2);
     ransac_select_kernel<<<n_problems, 256, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, best_.p, mask_dev,
                                                     small_.p, results_dev, iters, thr2, confidence);
@@ -478,10 +517,10 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
         P2P_CUDA(cudaStreamSynchronize(s));
         float ms[4];
         for (int i = 0; i < 4; ++i) P2P_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-        fprintf(stderr, "pnp[%d problems] hyp %.3f  score %.3f  select %.3f  refit %.3f ms\n", n_problems, ms[0], ms[1], ms[2], ms[3]);
+        fprintf(stderr, "pnp[%d problems] hyp+score wave 1 %.3f  wave 2 %.3f  select %.3f  refit %.3f ms\n", n_problems, ms[0], ms[1], ms[2], ms[3]);
         for (auto e : ev) cudaEventDestroy(e);
     }
-    launches += 4;
+    launches += 2;
 }
 
 void PnpSolver::solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,

@@ -6,8 +6,9 @@
 // the reference; see epnp_core.cuh): float32 correspondences, 5-point subsets drawn with OpenCV's
 // fixed-seed RNG, squared float32 reprojection error <= thr^2, "accept if goodCount > max(best, 4)",
 // adaptive iteration count at the given confidence, final EPnP on all inliers in double.
-// All `iters` hypotheses are evaluated in parallel; the sequential accept/terminate rule is then
-// replayed in iteration order, which selects the same hypothesis OpenCV would have stopped at.
+// Hypotheses are evaluated in parallel, in two waves in iteration order ([0, 32), then the rest for the problems whose
+// loop has not ended by then); the sequential accept/terminate rule is replayed in iteration order, which selects the
+// same hypothesis OpenCV would have stopped at.
 //
 // Kernels: (1) one thread per hypothesis: 5-point EPnP (fp64); (2) one warp per hypothesis: score
 // all correspondences, warp-shuffle reduction of the inlier count; (3) replay + inlier mask;
@@ -36,6 +37,7 @@ struct PnpResult {
     int pad;
 };
 
+constexpr int kFirstWave = 32;      // hypotheses generated and scored before the first termination check
 constexpr int kSmallRefit = 32;     // consensus sets up to this size are refitted in OpenCV's exact serial operation order
 
 class PnpSolver {
@@ -59,6 +61,7 @@ class PnpSolver {
     DevBuf<int> counts_;   // [problems][iters]
     DevBuf<int> best_;     // [problems][2]
     DevBuf<int> small_;    // [problems][kSmallRefit] ascending inlier indices of small consensus sets
+    DevBuf<uint8_t> done_; // [problems] the replayed loop ended within the first wave of hypotheses
     int cap_problems_ = 0, cap_iters_ = 0;
     cudaStream_t stream_ = nullptr;
     DevBuf<float> h_obj_, h_img_;
