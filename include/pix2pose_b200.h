@@ -82,6 +82,23 @@ P2P_API int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, 
                    double confidence, double* rvec, double* tvec, double* R, int* n_inliers, uint8_t* inlier_mask,
                    int* iters_run);
 
+/* The same for a batch of independent problems in one device run -- the three stage-2 candidates of every detection
+ * (recognition.py:196-217) are such a batch.  Problem i owns the next counts[i] rows of the pooled obj_pts / img_pts arrays;
+ * K = one row-major 3x3 per problem (k_per_problem != 0) or one for all.  results[i] is what p2p_pnp_ransac returns for
+ * problem i (status 1 = pose, 0 = OpenCV would return inliers=None, -1 = fewer than 6 points); inlier_mask (sum of counts
+ * bytes, may be NULL); *device_ms (may be NULL) = device time of the solve (CUDA events, copies excluded). */
+typedef struct p2p_pnp_result {
+    double rvec[3], tvec[3], R[9]; /* R = Rodrigues(rvec) */
+    int32_t n_inliers;             /* len(inliers), -1 without a model */
+    int32_t best_iter;             /* iteration whose hypothesis won */
+    int32_t iters_run;             /* iterations OpenCV's adaptive loop executes */
+    int32_t status;
+    int32_t n_mask, pad;
+} p2p_pnp_result_t;
+P2P_API int p2p_pnp_ransac_batch(const double* obj_pts, const double* img_pts, const int* counts, int n_problems,
+                         const double* K, int k_per_problem, float reproj_err, int iters, double confidence,
+                         p2p_pnp_result_t* results, uint8_t* inlier_mask, float* device_ms);
+
 /* ---- batched est_pose (recognition.py:70-193) ------------------------------------------------
  * One p2p_det_t per est_pose(rgb, bbox) call.  The host fills everything except pool_off / cap_px
  * (pix2pose_b200/recognition.py does the get_boxes arithmetic exactly as the reference). */

@@ -58,6 +58,8 @@ def lib():
         "p2p_predict_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
         "p2p_pnp_ransac": (ctypes.c_int, [c_d, c_d, ctypes.c_int, c_d, ctypes.c_float, ctypes.c_int, ctypes.c_double,
                                           c_d, c_d, c_d, c_i, ctypes.POINTER(ctypes.c_uint8), c_i]),
+        "p2p_pnp_ransac_batch": (ctypes.c_int, [c_d, c_d, c_i, ctypes.c_int, c_d, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                                ctypes.c_double, vp, ctypes.POINTER(ctypes.c_uint8), c_f]),
         "p2p_pipeline_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
         "p2p_pipeline_destroy": (None, [vp]),
         "p2p_pipeline_run": (ctypes.c_int, [vp, vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,

@@ -104,6 +104,17 @@ int p2p_pnp_ransac(const double* obj_pts, const double* img_pts, int n, const do
     });
 }
 
+static_assert(sizeof(p2p_pnp_result_t) == sizeof(PnpResult), "p2p_pnp_result_t mirrors PnpResult");
+
+int p2p_pnp_ransac_batch(const double* obj_pts, const double* img_pts, const int* counts, int n_problems, const double* K,
+                         int k_per_problem, float reproj_err, int iters, double confidence, p2p_pnp_result_t* results,
+                         uint8_t* inlier_mask, float* device_ms) {
+    return guarded([&] {
+        default_pnp().solve_host_batch(obj_pts, img_pts, counts, n_problems, K, k_per_problem, reproj_err, iters, confidence,
+                                       reinterpret_cast<PnpResult*>(results), inlier_mask, device_ms);
+    });
+}
+
 int p2p_pipeline_create(p2p_engine_t* e, int max_dets, int n_thresholds, p2p_pipeline_t** out) {
     return guarded([&] {
         P2P_CHECK(e && out, "NULL argument");

@@ -56,12 +56,12 @@ __device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t,
 __global__ void __launch_bounds__(kHypThreads, 1) ransac_hyp_kernel(const PnpProblem* __restrict__ probs, int n_problems,
                                                                  const float* __restrict__ obj, const float* __restrict__ img,
                                                                  double* __restrict__ hyp, int iters, int it0, int it1,
-                                                                 const uint8_t* __restrict__ done) {
+                                                                 const int* __restrict__ limit) {
     extern __shared__ double s_ws[];   // [144][kHypThreads]
     const long long gw = static_cast<long long>(blockIdx.x) * kHypThreads + threadIdx.x;   // flat over (problem, iteration of the wave)
     const int p = static_cast<int>(gw / (it1 - it0)), h = it0 + static_cast<int>(gw % (it1 - it0));
     if (p >= n_problems) return;
-    if (done && done[p]) return;       // OpenCV's loop ended in an earlier wave: it never draws this subset
+    if (limit && h >= limit[p]) return;   // OpenCV's loop ends before this iteration: it never draws this subset
     const long long g = static_cast<long long>(p) * iters + h;
     const PnpProblem pr = probs[p];
     if (pr.n < 6) return;
@@ -108,14 +108,15 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
                                                                        const float* __restrict__ obj,
                                                                        const float* __restrict__ img,
                                                                        const double* __restrict__ hyp, int* __restrict__ counts,
-                                                                       int iters, int it0, int it1, const uint8_t* __restrict__ done,
+                                                                       int iters, int it0, int it1, const int* __restrict__ limit,
                                                                        float thr2) {
     __shared__ float s_o[kScoreTile * 3];
     __shared__ float s_ip[kScoreTile * 2];
     const PnpProblem pr = probs[blockIdx.y];
     const int base = blockIdx.x * kScoreTile;
     if (pr.n < 6 || base >= pr.n) return;
-    if (done && done[blockIdx.y]) return;
+    if (limit) it1 = min(it1, limit[blockIdx.y]);
+    if (it0 >= it1) return;
     const int cnt_pts = min(kScoreTile, pr.n - base);
     const float* go = obj + (pr.offset + base) * 3;
     const float* gi = img + (pr.offset + base) * 2;
@@ -149,14 +150,14 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
 }
 
 // ---- (2b) between waves: has OpenCV's loop already ended?  The accept / adaptive-termination rule of
-// RANSACPointSetRegistrator::run replayed over the iterations scored so far; done[p] = 1 when `niters` fell to or below
-// the wave's end, i.e. the hypotheses of the later waves are ones OpenCV would never have generated.
+// RANSACPointSetRegistrator::run replayed over the iterations scored so far; limit[p] = `niters` at the wave's end (it only
+// ever decreases): iterations at or beyond it are ones OpenCV never runs, so the later waves skip them.
 __global__ void ransac_wave_check_kernel(const PnpProblem* __restrict__ probs, int n_problems, const int* __restrict__ counts,
-                                         uint8_t* __restrict__ done, int iters, int wave_end, double confidence) {
+                                         int* __restrict__ limit, int iters, int wave_end, double confidence) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_problems) return;
     const PnpProblem pr = probs[p];
-    if (pr.n < 6) { done[p] = 1; return; }
+    if (pr.n < 6) { limit[p] = 0; return; }
     int max_good = 0, niters = iters > 1 ? iters : 1;
     for (int it = 0; it < niters && it < wave_end; ++it) {
         const int c = counts[p * iters + it];
@@ -165,7 +166,7 @@ __global__ void ransac_wave_check_kernel(const PnpProblem* __restrict__ probs, i
             niters = ransac_update_num_iters(confidence, static_cast<double>(pr.n - c) / pr.n, 5, niters);
         }
     }
-    done[p] = niters <= wave_end ? 1 : 0;
+    limit[p] = niters;
 }
 
 // ---- (3) replay of RANSACPointSetRegistrator::run's accept / adaptive-termination rule + inlier mask
@@ -458,7 +459,7 @@ void PnpSolver::ensure(int n_problems, int iters) {
         counts_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_);
         best_.alloc(static_cast<size_t>(cap_problems_) * 2);
         small_.alloc(static_cast<size_t>(cap_problems_) * kSmallRefit);
-        done_.alloc(static_cast<size_t>(cap_problems_));
+        limit_.alloc(static_cast<size_t>(cap_problems_));
     }
 }
 
@@ -488,16 +489,16 @@ void PnpSolver::solve_batch(const PnpProblem* problems_dev, int n_problems, cons
     const dim3 g(std::max(1, (max_n + kScoreTile - 1) / kScoreTile), n_problems);
     for (int it0 = 0; it0 < iters; it0 = (it0 == 0 ? w1 : iters)) {
         const int it1 = it0 == 0 ? w1 : iters;
-        const uint8_t* done = it0 == 0 ? nullptr : done_.p;
+        const int* limit = it0 == 0 ? nullptr : limit_.p;
         const long long total = static_cast<long long>(n_problems) * (it1 - it0);
         ransac_hyp_kernel<<<static_cast<unsigned>((total + kHypThreads - 1) / kHypThreads), kHypThreads, hyp_smem, s>>>(
-            problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters, it0, it1, done);
+            problems_dev, n_problems, obj_dev, img_dev, hyp_.p, iters, it0, it1, limit);
         P2P_CUDA(cudaGetLastError());
-        ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, it0, it1, done, thr2);
+        ransac_score_kernel<<<g, kScoreWarps * 32, 0, s>>>(problems_dev, obj_dev, img_dev, hyp_.p, counts_.p, iters, it0, it1, limit, thr2);
         P2P_CUDA(cudaGetLastError());
         launches += 2;
         if (it1 < iters) {
-            ransac_wave_check_kernel<<<(n_problems + 127) / 128, 128, 0, s>>>(problems_dev, n_problems, counts_.p, done_.p, iters, it1, confidence);
+            ransac_wave_check_kernel<<<(n_problems + 127) / 128, 128, 0, s>>>(problems_dev, n_problems, counts_.p, limit_.p, iters, it1, confidence);
             P2P_CUDA(cudaGetLastError());
             ++launches;
             mark(1);
@@ -542,6 +543,51 @@ void PnpSolver::solve_host(const double* obj, const double* img, int n, const do
     P2P_CUDA(cudaMemcpyAsync(out, h_res_.p, sizeof(PnpResult), cudaMemcpyDeviceToHost, stream_));
     if (mask_out && n > 0) P2P_CUDA(cudaMemcpyAsync(mask_out, h_mask_.p, n, cudaMemcpyDeviceToHost, stream_));
     P2P_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void PnpSolver::solve_host_batch(const double* obj, const double* img, const int* counts, int n_problems, const double* K9,
+                                 int k_per_problem, float reproj_err, int iters, double confidence, PnpResult* out,
+                                 uint8_t* mask_out, float* device_ms) {
+    P2P_CHECK(n_problems >= 0, "negative problem count");
+    if (device_ms) *device_ms = 0.f;
+    if (n_problems == 0) return;
+    P2P_CHECK(obj && img && counts && K9 && out, "NULL argument");
+    std::vector<PnpProblem> pr(static_cast<size_t>(n_problems));
+    long long total = 0;
+    int max_n = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        P2P_CHECK(counts[i] >= 0, "problem %d: negative point count", i);
+        const double* K = K9 + (k_per_problem ? 9 * static_cast<size_t>(i) : 0);
+        pr[i].offset = total; pr[i].n = counts[i]; pr[i].pad = 0;
+        pr[i].fu = K[0]; pr[i].fv = K[4]; pr[i].uc = K[2]; pr[i].vc = K[5];
+        total += counts[i];
+        max_n = std::max(max_n, counts[i]);
+    }
+    std::vector<float> o(static_cast<size_t>(total) * 3), ip(static_cast<size_t>(total) * 2);
+    for (size_t i = 0; i < o.size(); ++i) o[i] = static_cast<float>(obj[i]);   // Mat::convertTo(CV_32F)
+    for (size_t i = 0; i < ip.size(); ++i) ip[i] = static_cast<float>(img[i]);
+    h_obj_.upload(o.data(), o.size(), stream_);
+    h_img_.upload(ip.data(), ip.size(), stream_);
+    if (h_mask_.n < static_cast<size_t>(total) + 1) h_mask_.alloc(static_cast<size_t>(total) + 1);
+    h_prob_.upload(pr.data(), pr.size(), stream_);
+    if (h_res_.n < static_cast<size_t>(n_problems)) h_res_.alloc(static_cast<size_t>(n_problems));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (device_ms) {
+        ensure(n_problems, iters);   // allocate outside the timed region
+        P2P_CUDA(cudaEventCreate(&e0));
+        P2P_CUDA(cudaEventCreate(&e1));
+        P2P_CUDA(cudaEventRecord(e0, stream_));
+    }
+    solve_batch(h_prob_.p, n_problems, h_obj_.p, h_img_.p, h_mask_.p, h_res_.p, reproj_err, iters, confidence, stream_, max_n);
+    if (device_ms) P2P_CUDA(cudaEventRecord(e1, stream_));
+    P2P_CUDA(cudaMemcpyAsync(out, h_res_.p, sizeof(PnpResult) * n_problems, cudaMemcpyDeviceToHost, stream_));
+    if (mask_out && total > 0) P2P_CUDA(cudaMemcpyAsync(mask_out, h_mask_.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost, stream_));
+    P2P_CUDA(cudaStreamSynchronize(stream_));
+    if (device_ms) {
+        P2P_CUDA(cudaEventElapsedTime(device_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
 }
 
 }  // namespace p2p

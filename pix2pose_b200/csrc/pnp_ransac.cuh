@@ -51,6 +51,11 @@ class PnpSolver {
     // Host convenience: one problem, double inputs converted to float32 like OpenCV does.
     void solve_host(const double* obj, const double* img, int n, const double* K9, float reproj_err, int iters,
                     double confidence, PnpResult* out, uint8_t* mask_out);
+    // Host convenience, batch: problem i owns the next counts[i] correspondences of the pooled arrays; K9 holds one 3x3 per
+    // problem (k_per_problem != 0) or one for all.  device_ms (may be NULL): the four-stage solve timed with CUDA events.
+    void solve_host_batch(const double* obj, const double* img, const int* counts, int n_problems, const double* K9,
+                          int k_per_problem, float reproj_err, int iters, double confidence, PnpResult* out, uint8_t* mask_out,
+                          float* device_ms);
     // Allocates the scratch for a batch up front (so that solve_batch can run inside a stream capture).
     void reserve(int n_problems, int iters) { ensure(n_problems, iters); }
     long long launches = 0;
@@ -61,7 +66,7 @@ class PnpSolver {
     DevBuf<int> counts_;   // [problems][iters]
     DevBuf<int> best_;     // [problems][2]
     DevBuf<int> small_;    // [problems][kSmallRefit] ascending inlier indices of small consensus sets
-    DevBuf<uint8_t> done_; // [problems] the replayed loop ended within the first wave of hypotheses
+    DevBuf<int> limit_;    // [problems] iteration bound (`niters`) of the replayed loop after the first wave of hypotheses
     int cap_problems_ = 0, cap_iters_ = 0;
     cudaStream_t stream_ = nullptr;
     DevBuf<float> h_obj_, h_img_;

@@ -76,6 +76,44 @@ def test_hypotheses_replay_cv2_on_hard_cases():
             assert np.array_equal(inl[:, 0], g[3][:, 0]), (trial, n, len(inl), len(g[3]))
 
 
+def test_batch_entry_point_equals_cv2_and_the_single_problem_call():
+    """p2p_pnp_ransac_batch: easy problems (the replayed loop ends within the first wave of 32 hypotheses and the second wave
+    is skipped for them) mixed with hard ones (all 100 iterations), empty / too small ones and per-problem camera matrices
+    in ONE launch sequence: every problem must come out as cv2.solvePnPRansac's, and bit-identical to the one-problem call."""
+    from pix2pose_b200.pnp import solve_pnp_ransac, solve_pnp_ransac_batch
+    rng = np.random.RandomState(11)
+    objs, imgs, Ks = [], [], []
+    for trial in range(48):
+        n = int(rng.choice([0, 3, 6, 9, 40, 300, 2500, 9000]))
+        of = float(rng.choice([0.0, 0.3, 0.7, 0.85]))
+        pw, uv = _planted(rng, max(n, 1), of, noise=float(rng.choice([0.5, 2.0])))
+        K = K_LM.copy()
+        K[0, 0] *= 1 + 0.01 * trial
+        K[1, 2] += trial
+        uv = (uv - [K_LM[0, 2], K_LM[1, 2]]) / [K_LM[0, 0], K_LM[1, 1]] * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]]
+        objs.append(pw[:n]); imgs.append(uv[:n]); Ks.append(K)
+    got = solve_pnp_ransac_batch(objs, imgs, np.stack(Ks))
+    early = late = 0
+    for i, (pw, uv, K, g) in enumerate(zip(objs, imgs, Ks, got)):
+        if len(pw) < 6:
+            assert g[3] is None, i
+            continue
+        ret, rv, tv, inl = cv2.solvePnPRansac(pw, uv.reshape(-1, 1, 2), K, None, flags=cv2.SOLVEPNP_EPNP, reprojectionError=5,
+                                              iterationsCount=100)
+        assert (inl is None) == (g[3] is None), i
+        one = solve_pnp_ransac(pw, uv, K)
+        assert g[5] == one[5]
+        early += g[5] <= 32
+        late += g[5] == 100
+        if inl is None:
+            continue
+        assert np.array_equal(inl[:, 0], g[3][:, 0]), (i, len(pw), len(inl), len(g[3]))
+        assert np.array_equal(g[1], one[1]) and np.array_equal(g[2], one[2]) and np.array_equal(g[4], one[4]), i
+        assert np.linalg.norm(g[2] - tv) <= 1e-9 * np.linalg.norm(tv), i
+    assert early >= 8 and late >= 8, (early, late)      # both sides of the wave split were exercised
+    assert solve_pnp_ransac_batch([], [], K_LM) == []
+
+
 def test_edge_cases():
     from pix2pose_b200.pnp import solve_pnp_ransac
     rng = np.random.RandomState(1)
