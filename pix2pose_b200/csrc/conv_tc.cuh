@@ -67,6 +67,7 @@ struct ConvParams {
     int epi_bufs;    // top ones to the epilogue as extra output staging tiles (epi_bufs = 1..3 tiles of EPI_BYTES)
     int dbg;         // bottleneck experiments on the persistent kernel (WRONG RESULTS): bit0 skip A loads, bit1 skip B loads,
                      // bit2 MMA issuer does not wait for operands
+    int a_sw64;      // persistent kernel: A tiles are 128 rows x 64 bytes in the 64-byte swizzle (stem: K <= 32 per k-iteration)
     int slab_ksize;  // slab kernel (conv_tc_slab.cuh): kernel size; p.kit then holds the slab table, kstart[1] = #entries
     int splitk_chunk;
     float* out_partial;

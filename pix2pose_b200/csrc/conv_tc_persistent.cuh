@@ -397,7 +397,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                 mbar_wait(&empty_bar[st], ph ^ 1);
                 uint8_t* sA = smem + st * Cfg::STAGE_BYTES;
                 uint8_t* sB = sA + Cfg::A_BYTES;
-                const uint32_t tx = ((p.dbg & 1) ? 0 : Cfg::A_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
+                const uint32_t tx = ((p.dbg & 1) ? 0 : (p.a_sw64 ? Cfg::A_BYTES / 2 : Cfg::A_BYTES)) + ((p.dbg & 2) ? 0 : Cfg::B_BYTES);
                 const int mi = k.x & 0xff;
                 const CUtensorMap* mA = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
                 if (elect_one()) {
@@ -460,8 +460,8 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_
                 // One elected region per k-iteration (<= 4 k16 steps, unrolled): the ELECT / BRA.DIV / BSYNC sequence and the
                 // descriptor set-up are paid once, not per k16 step -- narrow tiles (heads N = 16, stem, ResNet 1x1) were bound
                 // by this issue loop (~100 cycles per MMA), not by the tensor pipe.  Descriptors advance by 32 bytes = 2 units.
-                const uint64_t dA = umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
-                const uint64_t dAlo = umma_desc_sw128(aA + 128 * 128), dBlo = umma_desc_sw128(aB + BN * 128);
+                const uint64_t dA = p.a_sw64 ? umma_desc_sw64(aA) : umma_desc_sw128(aA), dB = umma_desc_sw128(aB);
+                const uint64_t dAlo = p.a_sw64 ? umma_desc_sw64(aA + 128 * 64) : umma_desc_sw128(aA + 128 * 128), dBlo = umma_desc_sw128(aB + BN * 128);
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {

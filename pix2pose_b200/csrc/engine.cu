@@ -383,6 +383,12 @@ void finalize_conv(const Plan& P, const std::vector<LayerDef>& L, ConvSpec& c) {
 
 // padded row width of the stem input in pixels: the last window starts at pixel 2 * 63 and is 16 pixels wide
 constexpr int kStemWp = 144;
+// The stem's K slice per kernel row is ksize * 4 <= 32 fp16 values: with 64-byte windows (SWIZZLE_64B A tiles) TMA moves half
+// the bytes of the 128-byte ones (the stem is bound by exactly that traffic: the overlapping windows are re-fetched per pixel).
+static bool stem_sw64() {
+    const char* e = getenv("P2P_STEM_SW64");
+    return !e || atoi(e) != 0;
+}
 static bool stem_direct() {
     const char* e = getenv("P2P_STEM_DIRECT");  // 0 = im2col + 1x1 GEMM (the first implementation)
     return !e || atoi(e) != 0;
@@ -476,10 +482,10 @@ EncodeTiledFn encode_fn() {
 }
 
 void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box) {
+            const cuuint32_t* box, bool sw64 = false) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         throw Error(P2P_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu strides %llu %llu %llu %llu box %u %u %u %u %u base %p)",
@@ -544,6 +550,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
             const cuuint64_t plane_b = static_cast<cuuint64_t>(cap) * H * W * C * 2;
             cuuint64_t dims[5], str[4];
             cuuint32_t box[5] = {64, (cuuint32_t)c.tw, (cuuint32_t)c.th, (cuuint32_t)c.nb, (cuuint32_t)np};
+            bool sw64 = false;
             if (rq.view == 0) {
                 dims[0] = rq.climit; dims[1] = W; dims[2] = H; dims[3] = cap; dims[4] = np;
                 str[0] = C * 2; str[1] = W * C * 2; str[2] = H * W * C * 2; str[3] = plane_b;
@@ -551,7 +558,9 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 // stem input (N, 128, Wp, 4): dim0 = 64 consecutive fp16 values (16 pixels), dim1 = output column (window start
                 // advances 2 pixels = 16 bytes: overlapping windows), dim2 = input rows of one parity
                 base += static_cast<size_t>(rq.view - 7) * W * C;
-                dims[0] = 64; dims[1] = 64; dims[2] = H / 2; dims[3] = cap; dims[4] = np;
+                sw64 = stem_sw64();
+                dims[0] = box[0] = sw64 ? 32 : 64;
+                dims[1] = 64; dims[2] = H / 2; dims[3] = cap; dims[4] = np;
                 str[0] = 16; str[1] = 2 * W * C * 2; str[2] = H * W * C * 2; str[3] = plane_b;
             } else if (rq.view >= 1 && rq.view <= 4) {
                 const int py = (rq.view - 1) >> 1, px = (rq.view - 1) & 1;
@@ -563,7 +572,7 @@ Engine::Engine(int bb, int capacity, int precision) : backbone(bb), cap(capacity
                 dims[0] = K; dims[1] = 1; dims[2] = 1; dims[3] = cap; dims[4] = np;
                 str[0] = K * 2; str[1] = K * 2; str[2] = K * 2; str[3] = plane_b;
             }
-            encode(&rt.mapA[mi], base, 5, dims, str, box);
+            encode(&rt.mapA[mi], base, 5, dims, str, box, sw64);
         }
         for (size_t mi = c.maps.size(); mi < 4; ++mi) rt.mapA[mi] = rt.mapA[0];
         memset(rt.mapOut, 0, sizeof(rt.mapOut));
@@ -967,6 +976,7 @@ void Engine::forward(const Model& m, const float* x_dev, int n, float* dec_dev, 
                 p.single_acc = (np == 2 && max_steps <= single_acc_steps) ? 1 : 0;
             }
             if (const char* e = getenv("P2P_DBG")) p.dbg = atoi(e);
+            p.a_sw64 = (c.kind == K_STEM && stem_sw64()) ? 1 : 0;
             p.Cout_pad = c.Cout_pad;
             if (c.kind == K_CONVT_FUSED && c.act != ACT_HEADS) p.fused_cout = c.Cout / 4;
             if (c.splitk > 1) {

@@ -216,6 +216,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                      // layout type: SWIZZLE_128B
     return d;
 }
+// The same with 64-byte rows (32 fp16) in the 64-byte swizzle: 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;                      // layout type: SWIZZLE_64B
+    return d;
+}
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 accumulator, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4)            // c_format = F32
