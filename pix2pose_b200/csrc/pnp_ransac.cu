@@ -12,8 +12,11 @@ namespace {
 
 constexpr int kHypThreads = 192;     // x 144 doubles of shared-memory workspace per thread = 216 KB: one block per SM
 constexpr int kScoreWarps = 8;
-constexpr int kRefitThreads = 64;   // small blocks: the kernel is dominated by thread 0's serial 12x12 eigen / Gauss-Newton section, so what counts
-                                     // is how many problems are resident at once (8 blocks per SM = one wave for 768 problems: 1.17 -> 0.41 ms)
+constexpr int kRefitThreads = 32;    // one warp per problem: the kernel is dominated by the serial eigen / Gauss-Newton section of ONE thread per
+                                     // problem at 255 registers, so what counts is that all problems are resident at once (8 blocks per SM = one
+                                     // wave up to 1184 blocks; at 64 threads 768 problems took two waves: 0.99 -> 0.66 ms).  Fixed, not chosen per
+                                     // batch: the order of the block sums must not depend on the batch size (batch invariance).
+constexpr int kListCap = 1024;       // consensus sets up to this size are handed to the refit as an index list (no scan over all correspondences)
 
 // cv::projectPoints (no distortion) + PnPRansacCallback::computeError for one correspondence:
 // projection in double, stored as float32, squared error accumulated in float32 without FMA.
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
     __shared__ int s_wc[8], s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    int* list = small_list + blockIdx.x * kSmallRefit;
+    int* list = small_list + static_cast<long long>(blockIdx.x) * kListCap;
     for (int base = 0; base < pr.n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         const bool f = i < pr.n && reproj_err_f32(R, t, o + 3 * i, ip + 2 * i, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
         int off = s_cnt;
         for (int w = 0; w < (threadIdx.x >> 5); ++w) off += s_wc[w];
         off += __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-        if (f && off < kSmallRefit) list[off] = i;
+        if (f && off < kListCap) list[off] = i;
         __syncthreads();
         if (threadIdx.x == 0)
             for (int w = 0; w < 8; ++w) s_cnt += s_wc[w];
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const PnpProblem* __
 // ---- (4a) refit on a small consensus set (5 is the minimum the accept rule allows): M^T M is (nearly) rank deficient
 // again and the result depends on every rounding, so one thread per problem runs OpenCV's exact serial operation order
 // on the inliers in index order (solve_small, the routine of the hypothesis kernel; workspace in shared memory).
-constexpr int kSmallThreads = 32;
+constexpr int kSmallThreads = 16;   // x 144 doubles of workspace = 18 KB of shared memory per block (of either kind): 8 blocks per SM fit
 __device__ __forceinline__ void refit_small_block(int block, const PnpProblem* __restrict__ probs, int n_problems,
                                                   const float* __restrict__ obj, const float* __restrict__ img,
                                                   const int* __restrict__ small_list, PnpResult* __restrict__ res, double* s_ws) {
@@ -259,7 +262,7 @@ __device__ __forceinline__ void refit_small_block(int block, const PnpProblem* _
     const int m = out->n_mask;
     const float* o = obj + pr.offset * 3;
     const float* ip = img + pr.offset * 2;
-    const int* list = small_list + p * kSmallRefit;
+    const int* list = small_list + static_cast<long long>(p) * kListCap;
     const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
     const double ifx = 1.0 / pr.fu, ify = 1.0 / pr.fv;
     double pws[kSmallRefit * 3], us[kSmallRefit * 2], Rk[3][3], tk[3], rv[3], Rf[3][3];
@@ -302,9 +305,9 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red, double* s
 }
 
 // Blocks 0 .. n_problems-1: one problem each (block reductions over its inliers).  The blocks after them run the exact serial
-// refits of the small consensus sets (4a), 32 problems per block, CONCURRENTLY with the large ones: both are bound by one
+// refits of the small consensus sets (4a), 16 problems per block, CONCURRENTLY with the large ones: both are bound by one
 // thread's serial latency, so as separate launches they simply added up (0.6 + 1.0 ms per 768 problems).
-__global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpProblem* __restrict__ probs, int n_problems,
+__global__ void __launch_bounds__(kRefitThreads, 8) epnp_refit_kernel(const PnpProblem* __restrict__ probs, int n_problems,
                                                                    const float* __restrict__ obj, const float* __restrict__ img,
                                                                    const uint8_t* __restrict__ mask, const int* __restrict__ small_list,
                                                                    PnpResult* __restrict__ res) {
@@ -331,6 +334,12 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
     const float* ip = img + pr.offset * 2;
     const uint8_t* mk = mask + pr.offset;
     const epnp::Cam cam = {pr.fu, pr.fv, pr.uc, pr.vc};
+    // The inliers: the ascending index list the selection kernel left (consensus sets up to kListCap points -- a sparse set in a
+    // 16 k-point crop costs its own size per pass, not a scan of the mask), else the mask itself.
+    const bool use_list = out->n_mask <= kListCap;
+    const int* list = small_list + static_cast<long long>(blockIdx.x) * kListCap;
+    const int n_walk = use_list ? out->n_mask : pr.n;
+    auto inlier_at = [&](int j) -> int { return use_list ? list[j] : (mk[j] ? j : -1); };
     if (threadIdx.x == 0) s_first = 0x7fffffff;
     __syncthreads();
 
@@ -338,11 +347,13 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
     {
         double v[4] = {0, 0, 0, 0};
         int first = 0x7fffffff;
-        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
-            if (mk[i]) {
+        for (int j = threadIdx.x; j < n_walk; j += blockDim.x) {
+            const int i = inlier_at(j);
+            if (i >= 0) {
                 v[0] += o[3 * i]; v[1] += o[3 * i + 1]; v[2] += o[3 * i + 2]; v[3] += 1.0;
                 first = min(first, i);
             }
+        }
         atomicMin(&s_first, first);
         block_reduce<4>(v, s_red, s_sum);
     }
@@ -353,14 +364,16 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
     // pass B: scatter matrix PW0^T PW0
     {
         double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
-            if (mk[i]) {
+        for (int j = threadIdx.x; j < n_walk; j += blockDim.x) {
+            const int i = inlier_at(j);
+            if (i >= 0) {
                 const double d[3] = {o[3 * i] - c0[0], o[3 * i + 1] - c0[1], o[3 * i + 2] - c0[2]};
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) v[a * 3 + b] += d[a] * d[b];
             }
+        }
         block_reduce<9>(v, s_red, s_sum);
     }
     if (threadIdx.x == 0) {
@@ -377,8 +390,9 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
         double v[52];
 #pragma unroll
         for (int k = 0; k < 52; ++k) v[k] = 0;
-        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
-            if (mk[i]) {
+        for (int j = threadIdx.x; j < n_walk; j += blockDim.x) {
+            const int i = inlier_at(j);
+            if (i >= 0) {
                 const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
                 double a[4];
                 epnp::barycentric(s_ci, s_cws, p, a);
@@ -399,6 +413,7 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
 #pragma unroll
                     for (int c = 0; c < 3; ++c) v[40 + j * 3 + c] += a[j] * (p[c] - c0[c]);
             }
+        }
         block_reduce<52>(v, s_red, s_sum);
     }
     __shared__ epnp::RefitShared s_sh;
@@ -415,14 +430,16 @@ __global__ void __launch_bounds__(kRefitThreads, 4) epnp_refit_kernel(const PnpP
     // pass E: mean reprojection distance of each of the three candidates
     {
         double v[3] = {0, 0, 0};
-        for (int i = threadIdx.x; i < pr.n; i += blockDim.x)
-            if (mk[i]) {
+        for (int j = threadIdx.x; j < n_walk; j += blockDim.x) {
+            const int i = inlier_at(j);
+            if (i >= 0) {
                 const double p[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
                 const double u = (static_cast<double>(ip[2 * i]) - pr.uc) * ifx * pr.fu + pr.uc;
                 const double vv = (static_cast<double>(ip[2 * i + 1]) - pr.vc) * ify * pr.fv + pr.vc;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[c] += epnp::reproj_dist(s_R[c], s_t[c], p, u, vv, cam);
             }
+        }
         block_reduce<3>(v, s_red, s_sum);
     }
     if (threadIdx.x == 0) {
@@ -458,7 +475,7 @@ void PnpSolver::ensure(int n_problems, int iters) {
         hyp_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_ * 12);
         counts_.alloc(static_cast<size_t>(cap_problems_) * cap_iters_);
         best_.alloc(static_cast<size_t>(cap_problems_) * 2);
-        small_.alloc(static_cast<size_t>(cap_problems_) * kSmallRefit);
+        small_.alloc(static_cast<size_t>(cap_problems_) * kListCap);
         limit_.alloc(static_cast<size_t>(cap_problems_));
     }
 }
