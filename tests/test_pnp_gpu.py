@@ -114,6 +114,33 @@ def test_batch_entry_point_equals_cv2_and_the_single_problem_call():
     assert solve_pnp_ransac_batch([], [], K_LM) == []
 
 
+def test_other_iteration_counts_and_large_batches():
+    """iterationsCount below / just above the first wave of 32 hypotheses and far above it (one wave, a short second wave,
+    a long one), and a batch larger than what is resident at once (1500 problems): same consensus sets as cv2."""
+    from pix2pose_b200.pnp import solve_pnp_ransac, solve_pnp_ransac_batch
+    rng = np.random.RandomState(21)
+    for iters in (1, 10, 40, 50, 300):
+        for of in (0.2, 0.75):
+            pw, uv = _planted(rng, 400, of, noise=1.0)
+            ret, rv, tv, inl = cv2.solvePnPRansac(pw, uv.reshape(-1, 1, 2), K_LM, None, flags=cv2.SOLVEPNP_EPNP,
+                                                  reprojectionError=5, iterationsCount=iters)
+            g = solve_pnp_ransac(pw, uv, K_LM, 5.0, iters, 0.99)
+            assert (inl is None) == (g[3] is None), (iters, of)
+            assert g[5] <= iters
+            if inl is not None:
+                assert np.array_equal(inl[:, 0], g[3][:, 0]), (iters, of, len(inl), len(g[3]))
+    objs, imgs = [], []
+    for i in range(1500):
+        pw, uv = _planted(rng, int(rng.choice([8, 20, 33, 70])), float(rng.choice([0.0, 0.3])), noise=0.5)
+        objs.append(pw); imgs.append(uv)
+    got = solve_pnp_ransac_batch(objs, imgs, K_LM)
+    for i in list(range(0, 1500, 97)) + [1499]:
+        one = solve_pnp_ransac(objs[i], imgs[i], K_LM)
+        assert (one[3] is None) == (got[i][3] is None), i
+        if one[3] is not None:
+            assert np.array_equal(one[3], got[i][3]) and np.array_equal(one[1], got[i][1]) and np.array_equal(one[2], got[i][2]), i
+
+
 def test_edge_cases():
     from pix2pose_b200.pnp import solve_pnp_ransac
     rng = np.random.RandomState(1)
