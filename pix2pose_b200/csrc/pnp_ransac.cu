@@ -35,21 +35,22 @@ __device__ __forceinline__ float reproj_err_f32(const double* R, const double* t
 }
 
 // Inlier test for the scoring kernel: the same decision as reproj_err_f32(...) <= thr2, but evaluated in fp32 first;
-// only correspondences whose fp32 error lands within `margin` of the threshold (fp32 error bound ~1e-3 px^2 at
+// only correspondences whose fp32 error lands within `margin` of the threshold (fp32 error bound ~3e-3 px^2 at
 // 5 px) or is not finite are re-evaluated through the exact fp64 path.  Pf = float copy of the projection matrix
 // K [R|t] (rows 0-1 scaled by fu / fv, so no separate intrinsics multiply), row 2 = the depth.
-__device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t, const float* Pf, const float* o,
-                                               const float* ip, const PnpProblem& pr, float ucf, float vcf, float thr2) {
-    const float X = o[0], Y = o[1], Z = o[2];
-    const float x = fmaf(Pf[0], X, fmaf(Pf[1], Y, fmaf(Pf[2], Z, Pf[3])));
-    const float y = fmaf(Pf[4], X, fmaf(Pf[5], Y, fmaf(Pf[6], Z, Pf[7])));
-    const float z = fmaf(Pf[8], X, fmaf(Pf[9], Y, fmaf(Pf[10], Z, Pf[11])));
-    const float iz = __fdividef(1.0f, z);                       // approximate reciprocal: the margin below absorbs its error
-    const float dx = (ip[0] - ucf) - x * iz, dy = (ip[1] - vcf) - y * iz;
+__device__ __forceinline__ bool is_inlier_fast(const double* R, const double* t, const float* Pf, const float4 pt, float vrel,
+                                               const float* __restrict__ ip_exact, const PnpProblem& pr, float thr2, float margin) {
+    // pt = (X, Y, Z, u - uc), vrel = v - vc (the centre is subtracted once per tile, not per hypothesis)
+    const float x = fmaf(Pf[0], pt.x, fmaf(Pf[1], pt.y, fmaf(Pf[2], pt.z, Pf[3])));
+    const float y = fmaf(Pf[4], pt.x, fmaf(Pf[5], pt.y, fmaf(Pf[6], pt.z, Pf[7])));
+    const float z = fmaf(Pf[8], pt.x, fmaf(Pf[9], pt.y, fmaf(Pf[10], pt.z, Pf[11])));
+    float iz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(z));    // one MUFU: the margin below absorbs its error
+    const float dx = fmaf(-x, iz, pt.w), dy = fmaf(-y, iz, vrel);
     const float e = fmaf(dx, dx, dy * dy);
-    const float margin = 0.01f * thr2 + 0.05f;
     if (fabsf(e - thr2) > margin && fabsf(z) > 1e-3f) return e <= thr2;   // NaN/inf fall through to the exact path
-    return reproj_err_f32(R, t, o, ip, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;
+    const float o[3] = {pt.x, pt.y, pt.z};
+    return reproj_err_f32(R, t, o, ip_exact, pr.fu, pr.fv, pr.uc, pr.vc) <= thr2;   // image point as stored (global memory: rare)
 }
 
 // ---- (1) hypotheses: one 5-point EPnP per thread, flat over (problem, iteration).  Every thread replays OpenCV's
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
                                                                        const double* __restrict__ hyp, int* __restrict__ counts,
                                                                        int iters, int it0, int it1, const int* __restrict__ limit,
                                                                        float thr2) {
-    __shared__ float s_o[kScoreTile * 3];
-    __shared__ float s_ip[kScoreTile * 2];
+    __shared__ float4 s_pt[kScoreTile];   // (X, Y, Z, u - uc)
+    __shared__ float s_v[kScoreTile];     // v - vc
     const PnpProblem pr = probs[blockIdx.y];
     const int base = blockIdx.x * kScoreTile;
     if (pr.n < 6 || base >= pr.n) return;
@@ -123,11 +124,14 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
     const int cnt_pts = min(kScoreTile, pr.n - base);
     const float* go = obj + (pr.offset + base) * 3;
     const float* gi = img + (pr.offset + base) * 2;
-    for (int i = threadIdx.x; i < cnt_pts * 3; i += blockDim.x) s_o[i] = go[i];
-    for (int i = threadIdx.x; i < cnt_pts * 2; i += blockDim.x) s_ip[i] = gi[i];
+    const float ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
+    for (int i = threadIdx.x; i < cnt_pts; i += blockDim.x) {
+        s_pt[i] = make_float4(go[3 * i], go[3 * i + 1], go[3 * i + 2], gi[2 * i] - ucf);
+        s_v[i] = gi[2 * i + 1] - vcf;
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float ucf = static_cast<float>(pr.uc), vcf = static_cast<float>(pr.vc);
+    const float margin = 0.01f * thr2 + 0.05f;   // fp32 evaluation error at 5 px: ~3e-3 px^2
     for (int h = it0 + warp; h < it1; h += kScoreWarps) {
         const double* m = hyp + (static_cast<long long>(blockIdx.y) * iters + h) * 12;
         double R[9], t[3];
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32) ransac_score_kernel(const Pn
         Pf[3] = static_cast<float>(t[0] * pr.fu); Pf[7] = static_cast<float>(t[1] * pr.fv); Pf[11] = static_cast<float>(t[2]);
         int cnt = 0;
         for (int i = lane; i < cnt_pts; i += 32)
-            cnt += is_inlier_fast(R, t, Pf, s_o + 3 * i, s_ip + 2 * i, pr, ucf, vcf, thr2) ? 1 : 0;  // NaN -> exact path -> false
+            cnt += is_inlier_fast(R, t, Pf, s_pt[i], s_v[i], gi + 2 * i, pr, thr2, margin) ? 1 : 0;  // NaN -> exact path -> false
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0 && cnt) atomicAdd(&counts[blockIdx.y * iters + h], cnt);
