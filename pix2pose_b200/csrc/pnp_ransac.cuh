@@ -10,9 +10,11 @@
 // loop has not ended by then); the sequential accept/terminate rule is replayed in iteration order, which selects the
 // same hypothesis OpenCV would have stopped at.
 //
-// Kernels: (1) one thread per hypothesis: 5-point EPnP (fp64); (2) one warp per hypothesis: score
-// all correspondences, warp-shuffle reduction of the inlier count; (3) replay + inlier mask;
-// (4) one CTA per problem: EPnP refit on the inliers (block reductions of the 12x12 normal matrix).
+// Kernels: (1) one thread per hypothesis: 5-point EPnP (fp64, OpenCV's operation order); (2) one warp per hypothesis:
+// score all correspondences, warp-shuffle reduction of the inlier count; (2b) between the two waves: replay of the
+// termination rule -> per-problem iteration bound; (3) replay + inlier mask + ascending inlier index list;
+// (4) one warp per problem: EPnP refit on the inliers (block sums of the structured 12x12 normal matrix, serial
+// eigen / Gauss-Newton tail), small consensus sets in OpenCV's exact serial order.
 #pragma once
 #include <stdint.h>
 
